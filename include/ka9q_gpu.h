@@ -1,0 +1,113 @@
+/* include/ka9q_gpu.h -- low-level C-ABI of libka9qgpu.so: the B200 overlap-save channelizer.
+ *
+ * Plain pointers and sizes only; no CUDA or torch types in the signatures (streams are passed
+ * as void* holding a cudaStream_t, device buffers as void*).  The reference-compatible
+ * filter.h surface (include/ka9q_gpu_filter.h) is implemented on top of these calls; bench.py
+ * and the multi-GPU harness call them directly so that device buffers owned by the caller
+ * (e.g. torch tensors that an NCCL broadcast fills) can be used in place.
+ *
+ * Every entry point names the reference code it replaces (paths relative to the ka9q-radio
+ * tree, commit 4e0033b4).  All functions return 0 on success, -1 on error (the reference's
+ * convention, filter.h:99-118) unless stated; kgpu_last_error() gives the text.
+ * There is NO CPU fallback: if no sm_100 device is usable the calls fail.
+ */
+#ifndef KA9Q_GPU_H
+#define KA9Q_GPU_H 1
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum kgpu_type { KGPU_COMPLEX = 1, KGPU_REAL = 2 }; /* same values as enum filtertype, filter.h:29-34 */
+enum kgpu_format {
+  KGPU_FMT_F32 = 0, /* float samples (REAL master) or float I/Q pairs (COMPLEX master): what drivers
+                       leave in the ring today (rx888.c:800-809, sig_gen.c:290-296) */
+  KGPU_FMT_I16 = 1  /* raw int16 samples / int16 I/Q pairs: the fused ingest (rx888.c:753-767) */
+};
+enum kgpu_chan_flags {
+  KGPU_CHAN_ISB = 1 /* filter_out.isb, filter.c:895-909 */
+};
+
+typedef struct kgpu_master kgpu_master; /* geometry + plans of one struct filter_in */
+typedef struct kgpu_bank kgpu_bank;     /* a batch of struct filter_out sharing one master */
+
+struct kgpu_ingest_stats { /* per block, only for KGPU_FMT_I16: rx888.c:759-762 */
+  unsigned long long energy; /* sum of x*x over the L new samples */
+  unsigned int clips;        /* |x| > 32766 */
+  unsigned int pad;
+};
+
+const char *kgpu_last_error(void);
+/* Number of this library's own kernels launched by the calling process so far (bench.py's
+ * "gpu_launches" claim is read from here, not estimated). */
+unsigned long long kgpu_launch_count(void);
+int kgpu_device_count(void);
+int kgpu_set_device(int device);
+
+/* ---- master: replaces create_filter_input's planning (filter.c:186-269) ------------------- */
+/* L new samples per block, impulse length M, N = L+M-1 (radio.c:582-587).  REAL needs even N. */
+kgpu_master *kgpu_master_create(int L, int M, int in_type);
+void kgpu_master_destroy(kgpu_master *m);
+int kgpu_master_points(kgpu_master const *m);       /* N */
+int kgpu_master_bins(kgpu_master const *m);         /* REAL: N/2+1, COMPLEX: N (filter.c:197) */
+long kgpu_master_spec_stride(kgpu_master const *m); /* float2 elements between consecutive block spectra */
+/* Plan description for logs/DESIGN.md: "n1 x n2, radices ..." */
+int kgpu_master_describe(kgpu_master const *m, char *buf, int buflen);
+
+/* Forward transform of `nblocks` consecutive overlap-save windows (replaces run_fft's
+ * fftwf_execute_dft_r2c / fftwf_execute_dft, filter.c:505-508, fused with the int16->float
+ * conversion rx888.c:753-767 when fmt == KGPU_FMT_I16).
+ *   d_in   device pointer to the first sample of block 0's WINDOW, i.e. M-1 samples before block
+ *          0's first new sample; window b starts b*L samples later (overlap-save, filter.c:631-635).
+ *          Units: float / int16 for REAL masters, (re,im) pairs for COMPLEX masters.
+ *   scale  multiplies int16 samples (rx888.c:765); ignored for float input.
+ *   d_spec nblocks * spec_stride float2; bins 0..bins-1 of each block, unnormalised, sign -1.
+ *   d_stats NULL or nblocks kgpu_ingest_stats (int16 only), zeroed by the call. */
+int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float scale, int derandomize, int nblocks,
+                 void *d_spec, void *d_stats, void *stream);
+
+/* Notch EWMA on listed bins (apply_notch_filters, filter.c:464-474); list ends with bin 0. The state
+ * lives in the master; blocks are processed in order. */
+int kgpu_master_set_notches(kgpu_master *m, int const *bins, double const *alpha, int n);
+int kgpu_apply_notches(kgpu_master *m, void *d_spec, int nblocks, void *stream);
+
+/* ---- bank: replaces create_filter_output / set_filter / execute_filter_output ------------- */
+kgpu_bank *kgpu_bank_create(kgpu_master *m, int capacity);
+void kgpu_bank_destroy(kgpu_bank *b);
+/* (Re)define channel idx: olen output samples per block (points = olen*N/L must be integral,
+ * filter.c:312-316), COMPLEX output.  Returns points, or -1. */
+int kgpu_bank_define(kgpu_bank *b, int idx, int olen);
+/* set_filter (filter.c:968-1045): Kaiser-windowed sinc designed on the host in double, forward
+ * transformed on the device.  low/high are fractions of the output rate. */
+int kgpu_bank_set_filter(kgpu_bank *b, int idx, double low, double high, double kaiser_beta);
+/* Caller-supplied frequency response (points complex floats), e.g. for tests. */
+int kgpu_bank_set_response(kgpu_bank *b, int idx, float const *response);
+int kgpu_bank_get_response(kgpu_bank *b, int idx, float *response); /* device -> host copy */
+/* shift as passed to execute_filter_output (filter.c:663); flags = kgpu_chan_flags. */
+int kgpu_bank_set_shift(kgpu_bank *b, int idx, int shift);
+int kgpu_bank_set_flags(kgpu_bank *b, int idx, int flags);
+int kgpu_bank_enable(kgpu_bank *b, int idx, int enabled);
+int kgpu_bank_channels(kgpu_bank const *b);          /* highest defined idx + 1 */
+long kgpu_bank_out_stride(kgpu_bank const *b);        /* float2 per block of the packed output row */
+long kgpu_bank_out_offset(kgpu_bank const *b, int idx); /* float2 offset of channel idx inside a row */
+/* Batched slice x response -> inverse transform -> keep last olen (filter.c:728-921) for every
+ * enabled channel and `nblocks` spectra.  d_out: nblocks * out_stride float2. */
+int kgpu_bank_run(kgpu_bank *b, const void *d_spec, int nblocks, void *d_out, void *stream);
+/* Single channel, single block (the retune slow path of the filter.h layer). d_out: olen float2. */
+int kgpu_bank_run_one(kgpu_bank *b, int idx, const void *d_spec, void *d_out, void *stream);
+
+/* Planner introspection, pure host code (works without a GPU): the in-register radices chosen for
+ * a column transform of length len (returns their count, -1 if unplannable) and the two-pass split
+ * n = n1*n2 of a long transform. */
+int kgpu_plan_radices(int len, int *radices, int max);
+int kgpu_plan_split(long n, int *n1, int *n2);
+
+/* Algorithmic bytes per block of one forward + all enabled channels. */
+double kgpu_algorithmic_bytes(kgpu_master const *m, kgpu_bank const *b, int fmt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

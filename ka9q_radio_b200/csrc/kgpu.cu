@@ -1,0 +1,760 @@
+// kgpu.cu -- host side of libka9qgpu.so: plan registry, forward-transform and channel-bank
+// launchers behind the C-ABI declared in include/ka9q_gpu.h.  No CPU fallback anywhere: every
+// entry point either launches the sm_100a kernels or fails with -1.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ka9q_gpu.h"
+#include "chan_kernels.cuh"
+#include "fwd_kernels.cuh"
+#include "plan.cuh"
+
+using namespace kfft;
+
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<unsigned long long> g_launches{0};
+
+static int fail(char const *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return -1;
+}
+#define CUDA_OK(expr)                                                                    \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess) return fail("%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+#define CUDA_OKP(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      fail("%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);         \
+      return nullptr;                                                                    \
+    }                                                                                    \
+  } while (0)
+
+extern "C" const char *kgpu_last_error(void) { return g_err.c_str(); }
+extern "C" unsigned long long kgpu_launch_count(void) { return g_launches.load(); }
+extern "C" int kgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+extern "C" int kgpu_set_device(int device) {
+  CUDA_OK(cudaSetDevice(device));
+  return 0;
+}
+
+// ------------------------------------------------------------------ radix selection ---------
+namespace kfft {
+
+static int const kRadixSet[] = {25, 24, 20, 16, 15, 12, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+
+// exhaustive search over multisets of supported radices (depth <= kMaxStages): fewest stages,
+// then smallest sum.
+static void search(int n, int start, std::vector<int> &cur, std::vector<int> &best, int &best_sum) {
+  if (n == 1) {
+    int sum = 0;
+    for (int r : cur) sum += r;
+    if (best.empty() || cur.size() < best.size() || (cur.size() == best.size() && sum < best_sum)) {
+      best = cur;
+      best_sum = sum;
+    }
+    return;
+  }
+  if ((int)cur.size() >= kMaxStages) return;
+  if (!best.empty() && cur.size() + 1 > best.size()) return;
+  for (int i = start; i < (int)(sizeof kRadixSet / sizeof kRadixSet[0]); i++) {
+    int const r = kRadixSet[i];
+    if (n % r) continue;
+    cur.push_back(r);
+    search(n / r, i, cur, best, best_sum);
+    cur.pop_back();
+  }
+}
+
+std::vector<int> choose_radices(int n) {
+  std::vector<int> cur, best;
+  int best_sum = 0;
+  if (n < 2) return best;
+  search(n, 0, cur, best, best_sum);
+  // even radices first (descending), odd last (descending): large strides first keeps the
+  // power-of-two strides away from the last, unit-stride stages
+  std::stable_sort(best.begin(), best.end(), [](int a, int b) {
+    bool const ea = (a % 2 == 0), eb = (b % 2 == 0);
+    if (ea != eb) return ea;
+    return a > b;
+  });
+  return best;
+}
+
+struct PlanSlot {
+  int len = 0;
+  TilePlan host;  // device pointers inside
+};
+static std::mutex g_plan_mu;
+static std::vector<PlanSlot> g_plans;
+
+int get_tile_plan(int len) {
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  for (size_t i = 0; i < g_plans.size(); i++)
+    if (g_plans[i].len == len) return (int)i;
+  if ((int)g_plans.size() >= kMaxPlans || len < 1 || len > 65535) return -1;
+  std::vector<int> rad;
+  if (len > 1) {
+    rad = choose_radices(len);
+    if (rad.empty()) return -1;
+  }
+  TilePlan p;
+  memset(&p, 0, sizeof p);
+  p.len = len;
+  p.nstages = (int)rad.size();
+  std::vector<float2> tw;
+  int n = len;
+  for (int i = 0; i < p.nstages; i++) {
+    int const r = rad[i], s = n / r;
+    p.radix[i] = r;
+    p.sub[i] = n;
+    p.stride[i] = s;
+    p.magic[i] = (s > 1) ? (uint32_t)(((1ull << 32) + (unsigned)s - 1) / (unsigned)s) : 0u;
+    p.tw_off[i] = (int)tw.size();
+    if (s > 1)
+      for (int t = 1; t < r; t++)
+        for (int j = 0; j < s; j++) {
+          long double const ang = -2.0L * M_PIl * (long double)((long)j * t % n) / (long double)n;
+          tw.push_back(make_float2((float)cosl(ang), (float)sinl(ang)));
+        }
+    n = s;
+  }
+  std::vector<uint16_t> perm((size_t)len);
+  for (int k = 0; k < len; k++) {
+    int rem = k, slot = 0;
+    for (int i = 0; i < p.nstages; i++) {
+      int const t = rem % p.radix[i];
+      rem /= p.radix[i];
+      slot += t * p.stride[i];
+    }
+    perm[k] = (uint16_t)slot;
+  }
+  float2 *d_tw = nullptr;
+  uint16_t *d_perm = nullptr;
+  if (cudaMalloc(&d_tw, sizeof(float2) * std::max<size_t>(tw.size(), 1)) != cudaSuccess) return -1;
+  if (cudaMalloc(&d_perm, sizeof(uint16_t) * (size_t)len) != cudaSuccess) return -1;
+  if (!tw.empty()) cudaMemcpy(d_tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice);
+  cudaMemcpy(d_perm, perm.data(), sizeof(uint16_t) * (size_t)len, cudaMemcpyHostToDevice);
+  p.tw = d_tw;
+  p.perm = d_perm;
+  int const idx = (int)g_plans.size();
+  if (cudaMemcpyToSymbol(c_plans, &p, sizeof p, sizeof(TilePlan) * (size_t)idx) != cudaSuccess) return -1;
+  PlanSlot sl;
+  sl.len = len;
+  sl.host = p;
+  g_plans.push_back(sl);
+  return idx;
+}
+TilePlan const *host_tile_plan(int idx) { return &g_plans[(size_t)idx].host; }
+
+static bool plannable(int len) { return len == 1 || (len <= kMaxTileLen && !choose_radices(len).empty()); }
+
+bool choose_split(long n, Split2 *out) {
+  long best = -1;
+  for (long d = (long)floor(sqrt((double)n) + 1e-9); d >= 1; d--) {
+    if (n % d) continue;
+    long const a = n / d;  // a >= d
+    if (a > kMaxTileLen) break;
+    if (plannable((int)a) && plannable((int)d)) {
+      best = d;
+      break;
+    }
+  }
+  if (best < 0) return false;
+  out->n1 = (int)(n / best);
+  out->n2 = (int)best;
+  return true;
+}
+}  // namespace kfft
+
+// ------------------------------------------------------------------ master ------------------
+struct kgpu_master {
+  int L, M, N, in_type, bins;
+  long nc;           // complex points of the two-pass transform (N/2 for REAL, N for COMPLEX)
+  Split2 sp;
+  int plan1, plan2, pitch1, pitch2;
+  long spec_stride;
+  RowItem *d_items = nullptr;
+  int n_item_ctas = 0;
+  float2 *d_rootD = nullptr;
+  float2 *d_mid = nullptr;
+  int mid_blocks = 0;
+  size_t smem1 = 0, smem2 = 0;
+  // notches
+  NotchDev *d_notch = nullptr;
+  int n_notch = 0;
+  int notch_sequential = 0;
+};
+
+static int set_smem(const void *func, size_t bytes) {
+  if (bytes > 48 * 1024)
+    CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
+  if (L < 1 || M < 1 || (in_type != KGPU_REAL && in_type != KGPU_COMPLEX)) {
+    fail("kgpu_master_create: bad arguments L=%d M=%d type=%d", L, M, in_type);
+    return nullptr;
+  }
+  int const N = L + M - 1;
+  if (in_type == KGPU_REAL && ((N & 1) || (L & 1))) {
+    fail("kgpu_master_create: REAL input needs even L and even N=L+M-1 (got L=%d N=%d)", L, N);
+    return nullptr;
+  }
+  kgpu_master *m = new kgpu_master;
+  m->L = L;
+  m->M = M;
+  m->N = N;
+  m->in_type = in_type;
+  m->bins = (in_type == KGPU_COMPLEX) ? N : N / 2 + 1;
+  m->nc = (in_type == KGPU_COMPLEX) ? N : N / 2;
+  if (!choose_split(m->nc, &m->sp)) {
+    fail("kgpu_master_create: %ld points cannot be split into two plannable lengths (factors 2,3,5,7; <= %d)",
+         m->nc, kMaxTileLen);
+    delete m;
+    return nullptr;
+  }
+  m->plan1 = get_tile_plan(m->sp.n1);
+  m->plan2 = get_tile_plan(m->sp.n2);
+  if (m->plan1 < 0 || m->plan2 < 0) {
+    fail("kgpu_master_create: plan registry full or length unsupported");
+    delete m;
+    return nullptr;
+  }
+  m->pitch1 = column_pitch(m->sp.n1);
+  m->pitch2 = column_pitch(m->sp.n2);
+  int const nit = (m->sp.n1 + 31) / 32;
+  m->smem1 = sizeof(float2) * ((size_t)kTile * m->pitch1 + (size_t)kTile * nit);
+  m->smem2 = sizeof(float2) * ((size_t)kTile * m->pitch2);
+  m->spec_stride = ((long)m->bins + 3) / 4 * 4;
+
+  // pass-2 work items
+  std::vector<RowItem> items;
+  int const n1 = m->sp.n1;
+  if (in_type == KGPU_REAL) {
+    items.push_back({kRowSelf0, 0, 0, 0});
+    for (int k1 = 1; 2 * k1 < n1; k1++) items.push_back({kRowPair, k1, n1 - k1, 0});
+    if (n1 % 2 == 0 && n1 > 1) items.push_back({kRowSelfMid, n1 / 2, n1 / 2, 0});
+    int const ipc = kTile / 2;
+    while (items.size() % ipc) items.push_back({kRowEmpty, 0, 0, 0});
+    m->n_item_ctas = (int)items.size() / ipc;
+  } else {
+    for (int k1 = 0; k1 < n1; k1++) items.push_back({kRowPlain, k1, 0, 0});
+    while (items.size() % kTile) items.push_back({kRowEmpty, 0, 0, 0});
+    m->n_item_ctas = (int)items.size() / kTile;
+  }
+  CUDA_OKP(cudaMalloc(&m->d_items, sizeof(RowItem) * items.size()));
+  CUDA_OKP(cudaMemcpy(m->d_items, items.data(), sizeof(RowItem) * items.size(), cudaMemcpyHostToDevice));
+  if (in_type == KGPU_REAL) {
+    std::vector<float2> rootD((size_t)m->sp.n2);
+    for (int k2 = 0; k2 < m->sp.n2; k2++) {
+      long double const ang = -M_PIl * (long double)k2 / (long double)m->sp.n2;
+      rootD[(size_t)k2] = make_float2((float)cosl(ang), (float)sinl(ang));
+    }
+    CUDA_OKP(cudaMalloc(&m->d_rootD, sizeof(float2) * rootD.size()));
+    CUDA_OKP(cudaMemcpy(m->d_rootD, rootD.data(), sizeof(float2) * rootD.size(), cudaMemcpyHostToDevice));
+  }
+  if (set_smem((const void *)fwd_cols_kernel<0>, m->smem1) || set_smem((const void *)fwd_cols_kernel<1>, m->smem1) ||
+      set_smem((const void *)fwd_rows_kernel, m->smem2)) {
+    kgpu_master_destroy(m);
+    return nullptr;
+  }
+  return m;
+}
+
+extern "C" void kgpu_master_destroy(kgpu_master *m) {
+  if (!m) return;
+  cudaFree(m->d_items);
+  cudaFree(m->d_rootD);
+  cudaFree(m->d_mid);
+  cudaFree(m->d_notch);
+  delete m;
+}
+extern "C" int kgpu_master_points(kgpu_master const *m) { return m ? m->N : -1; }
+extern "C" int kgpu_master_bins(kgpu_master const *m) { return m ? m->bins : -1; }
+extern "C" long kgpu_master_spec_stride(kgpu_master const *m) { return m ? m->spec_stride : -1; }
+extern "C" int kgpu_master_describe(kgpu_master const *m, char *buf, int buflen) {
+  if (!m || !buf) return -1;
+  std::string s;
+  char tmp[128];
+  snprintf(tmp, sizeof tmp, "N=%d %s, %ld-point complex two-pass %d x %d; cols radices [", m->N,
+           m->in_type == KGPU_REAL ? "real" : "complex", m->nc, m->sp.n1, m->sp.n2);
+  s += tmp;
+  TilePlan const *p1 = host_tile_plan(m->plan1), *p2 = host_tile_plan(m->plan2);
+  for (int i = 0; i < p1->nstages; i++) s += std::to_string(p1->radix[i]) + (i + 1 < p1->nstages ? "," : "");
+  s += "] rows radices [";
+  for (int i = 0; i < p2->nstages; i++) s += std::to_string(p2->radix[i]) + (i + 1 < p2->nstages ? "," : "");
+  snprintf(tmp, sizeof tmp, "]; smem %zu/%zu B; grids %d/%d CTAs per block", m->smem1, m->smem2,
+           (m->sp.n2 + kTile - 1) / kTile, m->n_item_ctas);
+  s += tmp;
+  snprintf(buf, (size_t)buflen, "%s", s.c_str());
+  return 0;
+}
+
+extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float scale, int derandomize, int nblocks,
+                            void *d_spec, void *d_stats, void *stream) {
+  if (!m || !d_in || !d_spec || nblocks < 1) return fail("kgpu_forward: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m->mid_blocks < nblocks) {
+    CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(m->d_mid);
+    m->d_mid = nullptr;
+    m->mid_blocks = 0;
+    CUDA_OK(cudaMalloc(&m->d_mid, sizeof(float2) * (size_t)m->nc * (size_t)nblocks));
+    m->mid_blocks = nblocks;
+  }
+  Pass1Args a1;
+  a1.in = d_in;
+  a1.hop = (m->in_type == KGPU_REAL) ? m->L / 2 : m->L;
+  a1.n1 = m->sp.n1;
+  a1.n2 = m->sp.n2;
+  a1.nc = m->nc;
+  a1.plan = m->plan1;
+  a1.pitch = m->pitch1;
+  a1.scale = scale;
+  a1.derandomize = derandomize;
+  a1.first_new = (m->in_type == KGPU_REAL) ? (m->M - 1) / 2 : (m->M - 1);
+  a1.mid = m->d_mid;
+  a1.stats = (fmt == KGPU_FMT_I16) ? (IngestStats *)d_stats : nullptr;
+  if (a1.stats) CUDA_OK(cudaMemsetAsync(d_stats, 0, sizeof(IngestStats) * (size_t)nblocks, st));
+  dim3 const g1((unsigned)((m->sp.n2 + kTile - 1) / kTile), (unsigned)nblocks);
+  if (fmt == KGPU_FMT_I16)
+    fwd_cols_kernel<1><<<g1, kFwdThreads, m->smem1, st>>>(a1);
+  else
+    fwd_cols_kernel<0><<<g1, kFwdThreads, m->smem1, st>>>(a1);
+  g_launches++;
+  Pass2Args a2;
+  a2.mid = m->d_mid;
+  a2.n1 = m->sp.n1;
+  a2.n2 = m->sp.n2;
+  a2.nc = m->nc;
+  a2.plan = m->plan2;
+  a2.pitch = m->pitch2;
+  a2.real_split = (m->in_type == KGPU_REAL);
+  a2.items = m->d_items;
+  a2.rootD = m->d_rootD;
+  a2.spec = (float2 *)d_spec;
+  a2.spec_stride = m->spec_stride;
+  dim3 const g2((unsigned)m->n_item_ctas, (unsigned)nblocks);
+  fwd_rows_kernel<<<g2, kFwdThreads, m->smem2, st>>>(a2);
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int kgpu_master_set_notches(kgpu_master *m, int const *bins, double const *alpha, int n) {
+  if (!m || n < 0) return fail("kgpu_master_set_notches: bad arguments");
+  cudaFree(m->d_notch);
+  m->d_notch = nullptr;
+  m->n_notch = 0;
+  if (n == 0) return 0;
+  std::vector<NotchDev> v((size_t)n);
+  m->notch_sequential = 0;
+  for (int i = 0; i < n; i++) {
+    if (bins[i] < 0 || bins[i] >= m->bins) return fail("kgpu_master_set_notches: bin %d out of range", bins[i]);
+    v[(size_t)i] = {bins[i], 0, 0.0, 0.0, alpha[i]};
+    for (int j = 0; j < i; j++)
+      if (bins[j] == bins[i]) m->notch_sequential = 1;
+  }
+  CUDA_OK(cudaMalloc(&m->d_notch, sizeof(NotchDev) * (size_t)n));
+  CUDA_OK(cudaMemcpy(m->d_notch, v.data(), sizeof(NotchDev) * (size_t)n, cudaMemcpyHostToDevice));
+  m->n_notch = n;
+  return 0;
+}
+extern "C" int kgpu_apply_notches(kgpu_master *m, void *d_spec, int nblocks, void *stream) {
+  if (!m || !d_spec) return fail("kgpu_apply_notches: bad arguments");
+  if (m->n_notch == 0) return 0;
+  notch_kernel<<<1, 32 * ((m->n_notch + 31) / 32), 0, (cudaStream_t)stream>>>(
+      m->d_notch, m->n_notch, m->notch_sequential, (float2 *)d_spec, m->spec_stride, nblocks);
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------ response design ----------
+// set_filter's host half (filter.c:968-1029, window.c:217-254, misc.c:416-427, misc.h:217-221,
+// sincospi.c:24-66): Kaiser-windowed sinc, complex-shifted to the passband centre, normalised for
+// window loss, the master's unnormalised forward transform and the half-power of a real input.
+namespace {
+double bessel_i0(double z) {
+  double const q = z * z / 4;
+  double sum = 1 + q, term = q;
+  for (int k = 2; k < 40; k++) {
+    term *= q / ((double)k * (double)k);
+    sum += term;
+    if (term < 1e-12 * sum) break;
+  }
+  return sum;
+}
+void cis_revolutions(double x, double *re, double *im) {  // exp(i*pi*x), exact reduction
+  double y = fmod(x, 2.0);
+  if (y < 0) y += 2.0;
+  int const quad = (int)floor(2.0 * y) & 3;
+  double z = y - 0.5 * quad;
+  bool const fold = z > 0.25;
+  if (fold) z = 0.5 - z;
+  double s = sin(M_PI * z), c = cos(M_PI * z);
+  if (fold) std::swap(s, c);
+  switch (quad) {
+    case 0: *re = c; *im = s; break;
+    case 1: *re = -s; *im = c; break;
+    case 2: *re = -c; *im = -s; break;
+    default: *re = s; *im = -c; break;
+  }
+}
+// taps[0..points) complex float (interleaved), first M = points-olen+1 non-zero
+int design_taps(int points, int olen, int master_points, bool master_real, double low, double high, double beta,
+                std::vector<float2> &taps) {
+  if (isnan(low) || isnan(high) || isnan(beta)) return -1;
+  if (low > high) std::swap(low, high);
+  low = std::min(std::max(low, -0.5), 0.5);
+  high = std::min(std::max(high, -0.5), 0.5);
+  int const M = points - olen + 1;
+  if (M < 2) return -1;
+  double const half_bw = (high == low) ? 1e-4 : fabs(high - low) / 2;
+  double const centre = (high + low) / 2;
+  std::vector<float> win((size_t)M);
+  double const norm0 = 1.0 / bessel_i0(beta), step = 2.0 / (M - 1);
+  for (int n = 0; n < M / 2; n++) {
+    double const p = step * n - 1;
+    win[(size_t)n] = win[(size_t)(M - 1 - n)] = (float)(bessel_i0(beta * sqrt(1 - p * p)) * norm0);
+  }
+  if (M & 1) win[(size_t)((M - 1) / 2)] = 1.0f;
+  double wsum = 0;
+  for (float w : win) wsum += w;
+  if (wsum == 0 || !std::isfinite(wsum)) return -1;
+  float const wgain = (float)(M / wsum);
+  for (float &w : win) w *= wgain;
+  taps.assign((size_t)points, make_float2(0.f, 0.f));
+  std::vector<double> rr((size_t)M), cr((size_t)M), ci((size_t)M);
+  double tap_sum = 0;
+  for (int i = 0; i < M; i++) {
+    double const n = i - (double)(M - 1) / 2;
+    double const arg = 2 * half_bw * n;
+    double const snc = (arg == 0) ? 1.0 : sin(M_PI * arg) / (M_PI * arg);
+    rr[(size_t)i] = win[(size_t)i] * 2 * half_bw * snc;
+    tap_sum += rr[(size_t)i];
+    cis_revolutions(2 * centre * n, &cr[(size_t)i], &ci[(size_t)i]);
+  }
+  double const gain = (master_real ? M_SQRT2 : 1.0) / (tap_sum * master_points);
+  for (int i = 0; i < M; i++) {
+    // the reference rounds the un-normalised tap to float first, then scales (filter.c:1015,1028)
+    float const tr = (float)(cr[(size_t)i] * rr[(size_t)i]), ti = (float)(ci[(size_t)i] * rr[(size_t)i]);
+    taps[(size_t)i] = make_float2((float)((double)tr * gain), (float)((double)ti * gain));
+  }
+  return 0;
+}
+}  // namespace
+
+// ------------------------------------------------------------------ bank --------------------
+struct ChanHost {
+  bool defined = false, enabled = false, has_response = false;
+  int olen = 0, points = 0, plan = -1, shift = 0, flags = 0;
+  long resp_off = 0;
+};
+struct kgpu_bank {
+  kgpu_master *m;
+  int capacity;
+  std::vector<ChanHost> ch;
+  int nchan = 0;  // highest defined + 1
+  float2 *d_resp = nullptr;
+  long resp_cap = 0, resp_used = 0;
+  ChanDesc *d_desc = nullptr;
+  std::vector<ChanDesc> desc;
+  std::vector<long> out_off;
+  long out_stride = 0;
+  bool dirty = true;
+  int max_points = 0;
+};
+
+static void resolve_walk(kgpu_master const *m, ChanHost const &c, ChanDesc &d) {
+  int const ns = c.points, mb = m->bins, half = ns / 2;
+  long const shift = c.shift;
+  d.zlead = 0;
+  d.ncopy = 0;
+  d.q0 = 0;
+  d.dir = 1;
+  if (m->in_type == KGPU_REAL) {
+    if (shift >= 0) {  // filter.c:819-855
+      long const start = shift - half;
+      long const z = std::min<long>(std::max<long>(0, -start), ns);
+      long const q0 = start + z;
+      long const nc = std::max<long>(0, std::min<long>(ns - z, (long)mb - q0));
+      d.zlead = (int)z;
+      d.q0 = (int)std::max<long>(0, std::min<long>(q0, mb - 1));
+      d.ncopy = (int)nc;
+    } else {  // filter.c:856-892
+      long const start = -(shift - half);
+      long const z = std::min<long>(std::max<long>(0, start - (mb - 1)), ns);
+      long const q0 = start - z;
+      long const nc = std::max<long>(0, std::min<long>(ns - z, q0 + 1));
+      d.zlead = (int)z;
+      d.q0 = (int)std::max<long>(0, std::min<long>(q0, mb - 1));
+      d.ncopy = (int)nc;
+      d.dir = -1;
+    }
+  } else {  // filter.c:728-793, the walk in closed form
+    long const nyq = (mb + 1) / 2;
+    long rp = shift - half;
+    long const z = std::min<long>(std::max<long>(0, -nyq - rp), ns);
+    d.zlead = (int)z;
+    if (z < ns) {
+      rp += z;
+      if (rp < 0) rp += mb;
+      if (rp >= 0 && rp < mb) {
+        long dist = ((nyq - rp - 1) % mb + mb) % mb + 1;
+        d.q0 = (int)rp;
+        d.ncopy = (int)std::min<long>(ns - z, dist);
+      }
+    }
+  }
+}
+
+static int bank_commit(kgpu_bank *b, cudaStream_t st) {
+  if (!b->dirty) return 0;
+  b->desc.assign((size_t)std::max(b->nchan, 1), ChanDesc{});
+  b->out_off.assign((size_t)std::max(b->nchan, 1), 0);
+  long off = 0;
+  b->max_points = 1;
+  for (int i = 0; i < b->nchan; i++) {
+    ChanHost const &c = b->ch[(size_t)i];
+    ChanDesc &d = b->desc[(size_t)i];
+    memset(&d, 0, sizeof d);
+    d.plan = -1;
+    b->out_off[(size_t)i] = off;
+    if (!c.defined) continue;
+    d.points = c.points;
+    d.olen = c.olen;
+    d.flags = c.flags;
+    d.resp_off = c.resp_off;
+    d.out_off = off;
+    off += c.olen;
+    if (c.enabled && c.has_response) {
+      d.plan = c.plan;
+      resolve_walk(b->m, c, d);
+      b->max_points = std::max(b->max_points, c.points);
+    }
+  }
+  b->out_stride = (off + 3) / 4 * 4;
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaMemcpy(b->d_desc, b->desc.data(), sizeof(ChanDesc) * b->desc.size(), cudaMemcpyHostToDevice));
+  b->dirty = false;
+  return 0;
+}
+
+extern "C" kgpu_bank *kgpu_bank_create(kgpu_master *m, int capacity) {
+  if (!m || capacity < 1) {
+    fail("kgpu_bank_create: bad arguments");
+    return nullptr;
+  }
+  kgpu_bank *b = new kgpu_bank;
+  b->m = m;
+  b->capacity = capacity;
+  b->ch.resize((size_t)capacity);
+  CUDA_OKP(cudaMalloc(&b->d_desc, sizeof(ChanDesc) * (size_t)capacity));
+  return b;
+}
+extern "C" void kgpu_bank_destroy(kgpu_bank *b) {
+  if (!b) return;
+  cudaFree(b->d_resp);
+  cudaFree(b->d_desc);
+  delete b;
+}
+static bool bad_idx(kgpu_bank const *b, int idx) { return !b || idx < 0 || idx >= b->capacity; }
+
+extern "C" int kgpu_bank_define(kgpu_bank *b, int idx, int olen) {
+  if (bad_idx(b, idx) || olen < 1) return fail("kgpu_bank_define: bad arguments");
+  long const num = (long)olen * b->m->N;
+  if (num % b->m->L) return fail("invalid output length %d for N=%d L=%d (filter.c:312-316)", olen, b->m->N, b->m->L);
+  int const points = (int)(num / b->m->L);
+  int const plan = get_tile_plan(points);
+  if (plan < 0) return fail("kgpu_bank_define: %d-point inverse transform cannot be planned", points);
+  ChanHost &c = b->ch[(size_t)idx];
+  if (!(c.defined && c.points == points)) {
+    long const need = (points + 3) / 4 * 4;
+    if (b->resp_used + need > b->resp_cap) {
+      long const ncap = std::max<long>(2 * b->resp_cap, b->resp_used + std::max<long>(need, 64L * 1024));
+      float2 *nb = nullptr;
+      CUDA_OK(cudaMalloc(&nb, sizeof(float2) * (size_t)ncap));
+      CUDA_OK(cudaDeviceSynchronize());
+      if (b->resp_used)
+        CUDA_OK(cudaMemcpy(nb, b->d_resp, sizeof(float2) * (size_t)b->resp_used, cudaMemcpyDeviceToDevice));
+      cudaFree(b->d_resp);
+      b->d_resp = nb;
+      b->resp_cap = ncap;
+    }
+    c.resp_off = b->resp_used;
+    b->resp_used += need;
+    c.has_response = false;
+  }
+  c.defined = true;
+  c.enabled = true;
+  c.olen = olen;
+  c.points = points;
+  c.plan = plan;
+  b->nchan = std::max(b->nchan, idx + 1);
+  b->dirty = true;
+  return points;
+}
+
+static int upload_taps_and_transform(kgpu_bank *b, ChanHost &c, float2 const *host, bool transform) {
+  float2 *dst = b->d_resp + c.resp_off;
+  // the response may be in use by a queued run: wait, then swap (the reference takes
+  // response_mutex for the same reason, filter.c:1039-1043)
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(dst, host, sizeof(float2) * (size_t)c.points, cudaMemcpyHostToDevice));
+  if (transform) {
+    size_t const sm = sizeof(float2) * (size_t)c.points;
+    if (set_smem((const void *)response_fft_kernel, sm)) return -1;
+    response_fft_kernel<<<1, 32, sm>>>(dst, c.plan);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaDeviceSynchronize());
+  }
+  c.has_response = true;
+  b->dirty = true;
+  return 0;
+}
+
+extern "C" int kgpu_bank_set_filter(kgpu_bank *b, int idx, double low, double high, double kaiser_beta) {
+  if (bad_idx(b, idx) || !b->ch[(size_t)idx].defined) return fail("kgpu_bank_set_filter: channel not defined");
+  ChanHost &c = b->ch[(size_t)idx];
+  std::vector<float2> taps;
+  if (design_taps(c.points, c.olen, b->m->N, b->m->in_type == KGPU_REAL, low, high, kaiser_beta, taps))
+    return fail("kgpu_bank_set_filter: rejected (NaN or M < 2), cf. filter.c:969,989");
+  return upload_taps_and_transform(b, c, taps.data(), true);
+}
+extern "C" int kgpu_bank_set_response(kgpu_bank *b, int idx, float const *response) {
+  if (bad_idx(b, idx) || !b->ch[(size_t)idx].defined || !response) return fail("kgpu_bank_set_response: bad arguments");
+  return upload_taps_and_transform(b, b->ch[(size_t)idx], (float2 const *)response, false);
+}
+extern "C" int kgpu_bank_get_response(kgpu_bank *b, int idx, float *response) {
+  if (bad_idx(b, idx) || !b->ch[(size_t)idx].has_response || !response) return fail("kgpu_bank_get_response: none");
+  ChanHost &c = b->ch[(size_t)idx];
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpy(response, b->d_resp + c.resp_off, sizeof(float2) * (size_t)c.points, cudaMemcpyDeviceToHost));
+  return c.points;
+}
+extern "C" int kgpu_bank_set_shift(kgpu_bank *b, int idx, int shift) {
+  if (bad_idx(b, idx) || !b->ch[(size_t)idx].defined) return fail("kgpu_bank_set_shift: channel not defined");
+  if (b->ch[(size_t)idx].shift != shift) {
+    b->ch[(size_t)idx].shift = shift;
+    b->dirty = true;
+  }
+  return 0;
+}
+extern "C" int kgpu_bank_set_flags(kgpu_bank *b, int idx, int flags) {
+  if (bad_idx(b, idx) || !b->ch[(size_t)idx].defined) return fail("kgpu_bank_set_flags: channel not defined");
+  if (b->ch[(size_t)idx].flags != flags) {
+    b->ch[(size_t)idx].flags = flags;
+    b->dirty = true;
+  }
+  return 0;
+}
+extern "C" int kgpu_bank_enable(kgpu_bank *b, int idx, int enabled) {
+  if (bad_idx(b, idx) || !b->ch[(size_t)idx].defined) return fail("kgpu_bank_enable: channel not defined");
+  if (b->ch[(size_t)idx].enabled != (enabled != 0)) {
+    b->ch[(size_t)idx].enabled = enabled != 0;
+    b->dirty = true;
+  }
+  return 0;
+}
+extern "C" int kgpu_bank_channels(kgpu_bank const *b) { return b ? b->nchan : -1; }
+extern "C" long kgpu_bank_out_stride(kgpu_bank const *b) {
+  if (!b) return -1;
+  if (b->dirty) bank_commit(const_cast<kgpu_bank *>(b), 0);
+  return b->out_stride;
+}
+extern "C" long kgpu_bank_out_offset(kgpu_bank const *b, int idx) {
+  if (bad_idx(b, idx)) return -1;
+  if (b->dirty) bank_commit(const_cast<kgpu_bank *>(b), 0);
+  return idx < b->nchan ? b->out_off[(size_t)idx] : -1;
+}
+
+static int launch_chan(kgpu_bank *b, const void *d_spec, int nblocks, void *d_out, long out_stride, int base, int n,
+                       cudaStream_t st) {
+  ChanArgs a;
+  a.spec = (float2 const *)d_spec;
+  a.spec_stride = b->m->spec_stride;
+  a.m_bins = b->m->bins;
+  a.wrap = (b->m->in_type == KGPU_COMPLEX);
+  a.desc = b->d_desc;
+  a.nchan = n;
+  a.chan_base = base;
+  a.resp = b->d_resp;
+  a.out = (float2 *)d_out;
+  a.out_stride = out_stride;
+  a.pitch = (b->max_points + 3) / 4 * 4 + 2;
+  size_t const sm = sizeof(float2) * (size_t)a.pitch * kChanWarps;
+  if (set_smem((const void *)chan_kernel, sm)) return -1;
+  dim3 const g((unsigned)((n + kChanWarps - 1) / kChanWarps), (unsigned)nblocks);
+  chan_kernel<<<g, kChanWarps * 32, sm, st>>>(a);
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int kgpu_bank_run(kgpu_bank *b, const void *d_spec, int nblocks, void *d_out, void *stream) {
+  if (!b || !d_spec || !d_out || nblocks < 1) return fail("kgpu_bank_run: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bank_commit(b, st)) return -1;
+  if (b->nchan == 0) return 0;
+  return launch_chan(b, d_spec, nblocks, d_out, b->out_stride, 0, b->nchan, st);
+}
+extern "C" int kgpu_bank_run_one(kgpu_bank *b, int idx, const void *d_spec, void *d_out, void *stream) {
+  if (bad_idx(b, idx) || !d_spec || !d_out) return fail("kgpu_bank_run_one: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bank_commit(b, st)) return -1;
+  // write this channel's olen samples at d_out[0..olen): shift the row origin back by out_off
+  float2 *origin = (float2 *)d_out - b->out_off[(size_t)idx];
+  return launch_chan(b, d_spec, 1, origin, 0, idx, 1, st);
+}
+
+// pure host helpers (usable without a GPU): what the planner would pick
+extern "C" int kgpu_plan_radices(int len, int *radices, int max) {
+  std::vector<int> r = choose_radices(len);
+  if (len != 1 && r.empty()) return -1;
+  for (int i = 0; i < (int)r.size() && i < max; i++) radices[i] = r[(size_t)i];
+  return (int)r.size();
+}
+extern "C" int kgpu_plan_split(long n, int *n1, int *n2) {
+  Split2 sp;
+  if (!choose_split(n, &sp)) return -1;
+  *n1 = sp.n1;
+  *n2 = sp.n2;
+  return 0;
+}
+
+extern "C" double kgpu_algorithmic_bytes(kgpu_master const *m, kgpu_bank const *b, int fmt) {
+  if (!m) return 0;
+  double const s_in = (m->in_type == KGPU_REAL) ? (fmt == KGPU_FMT_I16 ? 2.0 : 4.0) : (fmt == KGPU_FMT_I16 ? 4.0 : 8.0);
+  double bytes = (double)m->N * s_in + (double)m->bins * 8.0;
+  if (b)
+    for (int i = 0; i < b->nchan; i++) {
+      ChanHost const &c = b->ch[(size_t)i];
+      if (c.defined && c.enabled && c.has_response) bytes += 8.0 * (2.0 * c.points + c.olen);
+    }
+  return bytes;
+}
