@@ -43,6 +43,13 @@ const char *kgpu_last_error(void);
 /* Number of this library's own kernels launched by the calling process so far (bench.py's
  * "gpu_launches" claim is read from here, not estimated). */
 unsigned long long kgpu_launch_count(void);
+/* Per-launch profiling: when enabled every kernel launch is bracketed by CUDA events on its own
+ * stream; totals per kernel kind (index < kgpu_profile_kernels()) are read back after a sync. */
+int kgpu_profile_enable(int on);
+int kgpu_profile_reset(void);
+int kgpu_profile_kernels(void);
+const char *kgpu_profile_name(int kernel);
+int kgpu_profile_get(int kernel, double *total_ms, long *count);
 int kgpu_device_count(void);
 int kgpu_set_device(int device);
 
@@ -97,6 +104,12 @@ long kgpu_bank_out_offset(kgpu_bank const *b, int idx); /* float2 offset of chan
 int kgpu_bank_run(kgpu_bank *b, const void *d_spec, int nblocks, void *d_out, void *stream);
 /* Single channel, single block (the retune slow path of the filter.h layer). d_out: olen float2. */
 int kgpu_bank_run_one(kgpu_bank *b, int idx, const void *d_spec, void *d_out, void *stream);
+
+/* Push pending channel changes (shift/filter/enable) to the device now, ordered after `stream`. */
+int kgpu_bank_commit(kgpu_bank *b, void *stream);
+/* Testing aid: 0 forces the generic runtime-plan kernels even where a compile-time specialised
+ * kernel exists (both are parity-tested). Default 1. */
+int kgpu_use_static_kernels(int on);
 
 /* Planner introspection, pure host code (works without a GPU): the in-register radices chosen for
  * a column transform of length len (returns their count, -1 if unplannable) and the two-pass split

@@ -73,6 +73,12 @@ def load() -> C.CDLL:
     L.kgpu_bank_out_offset.restype = l
     L.kgpu_bank_run.argtypes = [vp, vp, i, vp, vp]
     L.kgpu_bank_run_one.argtypes = [vp, i, vp, vp, vp]
+    L.kgpu_bank_commit.argtypes = [vp, vp]
+    L.kgpu_use_static_kernels.argtypes = [i]
+    L.kgpu_profile_enable.argtypes = [i]
+    L.kgpu_profile_name.argtypes = [i]
+    L.kgpu_profile_name.restype = C.c_char_p
+    L.kgpu_profile_get.argtypes = [i, vp, vp]
     L.kgpu_plan_radices.argtypes = [i, vp, i]
     L.kgpu_plan_split.argtypes = [l, vp, vp]
     L.kgpu_algorithmic_bytes.argtypes = [vp, vp, i]
@@ -88,6 +94,17 @@ def exported_symbols() -> list[str]:
     hdr = (PKG.parent / "include" / "ka9q_gpu.h").read_text()
     hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)  # declarations only, not prose
     return sorted(set(re.findall(r"\b(kgpu_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def profile_snapshot() -> dict[str, tuple[float, int]]:
+    """{kernel name: (total ms, launches)} since the last kgpu_profile_reset()."""
+    L = load()
+    out = {}
+    for k in range(L.kgpu_profile_kernels()):
+        ms, cnt = C.c_double(0), C.c_long(0)
+        L.kgpu_profile_get(k, C.cast(C.pointer(ms), C.c_void_p), C.cast(C.pointer(cnt), C.c_void_p))
+        out[L.kgpu_profile_name(k).decode()] = (ms.value, cnt.value)
+    return out
 
 
 def plan_radices(length: int) -> list[int]:

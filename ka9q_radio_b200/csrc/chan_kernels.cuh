@@ -37,8 +37,9 @@ struct ChanArgs {
   int m_bins;        // master bins (wrap modulus for COMPLEX masters)
   int wrap;          // 1: COMPLEX master (q wraps mod m_bins), 0: REAL
   ChanDesc const *desc;
-  int nchan;
-  int chan_base;     // first descriptor to process (run_one)
+  int const *order;  // descriptor indices to process (one launch per plan), or nullptr:
+  int norder;        //   then descriptors chan_base .. chan_base+norder-1
+  int chan_base;
   float2 const *resp;
   float2 *out;
   long out_stride;
@@ -48,9 +49,9 @@ struct ChanArgs {
 __global__ void __launch_bounds__(kChanWarps * 32) chan_kernel(ChanArgs const a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int const ch = a.chan_base + blockIdx.x * kChanWarps + warp;
-  if (ch >= a.chan_base + a.nchan) return;
-  ChanDesc const d = a.desc[ch];
+  int const oi = blockIdx.x * kChanWarps + warp;
+  if (oi >= a.norder) return;
+  ChanDesc const d = a.desc[a.order ? a.order[oi] : a.chan_base + oi];
   if (d.plan < 0) return;
   int const blk = blockIdx.y;
   float2 *col = reinterpret_cast<float2 *>(smem_raw) + warp * a.pitch;
@@ -60,19 +61,41 @@ __global__ void __launch_bounds__(kChanWarps * 32) chan_kernel(ChanArgs const a)
 
   float2 const *X = a.spec + (long)blk * a.spec_stride;
   float2 const *R = a.resp + d.resp_off;
-  for (int wp = lane; wp < ns; wp += 32) {
+  auto src_of = [&](int wp, bool &live, bool &cj) -> int {
     int t = wp - top;
     if (t < 0) t += ns;
-    float2 v = make_float2(0.f, 0.f);
     int const u = t - d.zlead;
-    if (u >= 0 && u < d.ncopy && wp != top) {  // Nyquist slot is forced to zero (filter.c:911)
-      int q = d.q0 + d.dir * u;
-      if (a.wrap && q >= a.m_bins) q -= a.m_bins;
-      float2 x = __ldg(X + q);
-      if (d.dir < 0) x.y = -x.y;
-      v = cmul(x, __ldg(R + wp));
+    live = (u >= 0 && u < d.ncopy && wp != top);  // Nyquist slot is forced to zero (filter.c:911)
+    cj = d.dir < 0;
+    int q = d.q0 + d.dir * u;
+    if (a.wrap && q >= a.m_bins) q -= a.m_bins;
+    return live ? q : 0;
+  };
+  constexpr int U = 4;
+  int wp = lane;
+  for (; wp + (U - 1) * 32 < ns; wp += U * 32) {
+    float2 x[U], rr[U];
+    bool live[U], cj[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      int const q = src_of(wp + u * 32, live[u], cj[u]);
+      x[u] = __ldg(X + q);
+      rr[u] = __ldg(R + wp + u * 32);
     }
-    col[wp] = v;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (cj[u]) x[u].y = -x[u].y;
+      float2 const v = cmul(x[u], rr[u]);
+      col[wp + u * 32] = live[u] ? v : make_float2(0.f, 0.f);
+    }
+  }
+  for (; wp < ns; wp += 32) {
+    bool live, cj;
+    int const q = src_of(wp, live, cj);
+    float2 x = __ldg(X + q);
+    if (cj) x.y = -x.y;
+    float2 const v = cmul(x, __ldg(R + wp));
+    col[wp] = live ? v : make_float2(0.f, 0.f);
   }
   __syncwarp();
   if (d.flags & 1) {  // ISB: (S[p], S[ns-p]) <- (S[p]+conj S[ns-p], S[ns-p]-conj S[p]); S[0]=0
@@ -90,7 +113,21 @@ __global__ void __launch_bounds__(kChanWarps * 32) chan_kernel(ChanArgs const a)
   tile_fft<true>(pl, col, lane, 32, [] { __syncwarp(); });
   float2 *dst = a.out + (long)blk * a.out_stride + d.out_off;
   int const first = ns - d.olen;
-  for (int i = lane; i < d.olen; i += 32) dst[i] = col[__ldg(pl.perm + first + i)];
+  {
+    constexpr int V = 4;
+    int i = lane;
+    for (; i + (V - 1) * 32 < d.olen; i += V * 32) {
+      int slot[V];
+      float2 v[V];
+#pragma unroll
+      for (int u = 0; u < V; u++) slot[u] = __ldg(pl.perm + first + i + u * 32);
+#pragma unroll
+      for (int u = 0; u < V; u++) v[u] = col[slot[u]];
+#pragma unroll
+      for (int u = 0; u < V; u++) dst[i + u * 32] = v[u];
+    }
+    for (; i < d.olen; i += 32) dst[i] = col[__ldg(pl.perm + first + i)];
+  }
 }
 
 // Forward transform of one response in place (set_filter's fftwf_execute, filter.c:1030):

@@ -48,14 +48,20 @@ __device__ __forceinline__ void dif_stage(float2 *__restrict__ col, int len, int
     }
     float2 *p = col + b * nsub + j;
     float2 x[R];
+    constexpr bool kPrefetchTw = (R <= 12);  // bigger radices have no registers to spare
+    float2 w[kPrefetchTw ? R : 1];
+    if (kPrefetchTw && s > 1) {  // twiddles first: their (L1-resident) latency overlaps the butterfly
+#pragma unroll
+      for (int t = 1; t < R; t++) w[kPrefetchTw ? t : 0] = __ldg(tw + (t - 1) * s + j);
+    }
 #pragma unroll
     for (int m = 0; m < R; m++) x[m] = p[m * s];
     Dft<R, INV>::run(x);
     if (s > 1) {
 #pragma unroll
       for (int t = 1; t < R; t++) {
-        float2 const w = __ldg(tw + (t - 1) * s + j);
-        x[t] = INV ? cmulc(x[t], w) : cmul(x[t], w);
+        float2 const wt = kPrefetchTw ? w[kPrefetchTw ? t : 0] : __ldg(tw + (t - 1) * s + j);
+        x[t] = INV ? cmulc(x[t], wt) : cmul(x[t], wt);
       }
     }
 #pragma unroll

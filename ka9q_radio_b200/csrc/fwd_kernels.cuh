@@ -67,32 +67,48 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_cols_kernel(Pass1Args cons
   // ---- cooperative load: kTile adjacent columns x 32 rows per step ----------------------
   unsigned long long energy = 0;
   unsigned int clips = 0;
+  constexpr int U = 8;  // independent global loads in flight per thread
   if (FMT == 1) {
-    int const *src = reinterpret_cast<int const *>(a.in) + (long)blk * a.hop;
-    for (int n1 = r; n1 < a.n1; n1 += rows_per_it) {
-      float2 v = make_float2(0.f, 0.f);
-      if (col_ok) {
-        long const idx = (long)n1 * a.n2 + n2g;
-        int w = __ldg(src + idx);
-        short lo = (short)(w & 0xffff), hi = (short)((unsigned)w >> 16);
-        if (a.derandomize) {  // lsb set -> flip bits 1..15 (rx888.c:707-712)
-          lo ^= (short)((lo & 1) ? 0xfffe : 0);
-          hi ^= (short)((hi & 1) ? 0xfffe : 0);
-        }
-        if (a.stats && idx >= a.first_new) {
-          energy += (unsigned long long)((int)lo * lo) + (unsigned long long)((int)hi * hi);
-          clips += (lo > 32766 || lo < -32766) + (hi > 32766 || hi < -32766);
-        }
-        v = make_float2((float)lo * a.scale, (float)hi * a.scale);
+    int const *src = reinterpret_cast<int const *>(a.in) + (long)blk * a.hop + n2g;
+    auto put = [&](int n1, int w) {
+      short lo = (short)(w & 0xffff), hi = (short)((unsigned)w >> 16);
+      if (a.derandomize) {  // lsb set -> flip bits 1..15 (rx888.c:707-712)
+        lo ^= (short)((lo & 1) ? 0xfffe : 0);
+        hi ^= (short)((hi & 1) ? 0xfffe : 0);
       }
-      tile[c * a.pitch + n1] = v;
+      if (a.stats && (long)n1 * a.n2 + n2g >= a.first_new) {
+        energy += (unsigned long long)((int)lo * lo) + (unsigned long long)((int)hi * hi);
+        clips += (lo > 32766 || lo < -32766) + (hi > 32766 || hi < -32766);
+      }
+      tile[c * a.pitch + n1] = make_float2((float)lo * a.scale, (float)hi * a.scale);
+    };
+    int n1 = r;
+    if (col_ok) {
+      for (; n1 + (U - 1) * rows_per_it < a.n1; n1 += U * rows_per_it) {
+        int w[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) w[u] = __ldg(src + (long)(n1 + u * rows_per_it) * a.n2);
+#pragma unroll
+        for (int u = 0; u < U; u++) put(n1 + u * rows_per_it, w[u]);
+      }
+      for (; n1 < a.n1; n1 += rows_per_it) put(n1, __ldg(src + (long)n1 * a.n2));
+    } else {
+      for (; n1 < a.n1; n1 += rows_per_it) tile[c * a.pitch + n1] = make_float2(0.f, 0.f);
     }
   } else {
-    float2 const *src = reinterpret_cast<float2 const *>(a.in) + (long)blk * a.hop;
-    for (int n1 = r; n1 < a.n1; n1 += rows_per_it) {
-      float2 v = make_float2(0.f, 0.f);
-      if (col_ok) v = __ldg(src + (long)n1 * a.n2 + n2g);
-      tile[c * a.pitch + n1] = v;
+    float2 const *src = reinterpret_cast<float2 const *>(a.in) + (long)blk * a.hop + n2g;
+    int n1 = r;
+    if (col_ok) {
+      for (; n1 + (U - 1) * rows_per_it < a.n1; n1 += U * rows_per_it) {
+        float2 w[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) w[u] = __ldg(src + (long)(n1 + u * rows_per_it) * a.n2);
+#pragma unroll
+        for (int u = 0; u < U; u++) tile[c * a.pitch + n1 + u * rows_per_it] = w[u];
+      }
+      for (; n1 < a.n1; n1 += rows_per_it) tile[c * a.pitch + n1] = __ldg(src + (long)n1 * a.n2);
+    } else {
+      for (; n1 < a.n1; n1 += rows_per_it) tile[c * a.pitch + n1] = make_float2(0.f, 0.f);
     }
   }
   // inter-pass twiddle factors W_nc^{n2*k1}, k1 = r + 32*it, as B(n2,r) * A(n2,it)
@@ -124,12 +140,21 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_cols_kernel(Pass1Args cons
   if (col_ok) {
     float2 *dst = a.mid + (long)blk * a.nc + n2g;
     float2 const *colp = tile + c * a.pitch;
-    int it = 0;
-    for (int k1 = r; k1 < a.n1; k1 += rows_per_it, it++) {
-      float2 v = colp[__ldg(pl.perm + k1)];
-      float2 const w = cmul(twB, twA[c * nit + it]);
-      dst[(long)k1 * a.n2] = cmul(v, w);
+    float2 const *twc = twA + c * nit;
+    constexpr int V = 4;
+    int it = 0, k1 = r;
+    for (; k1 + (V - 1) * rows_per_it < a.n1; k1 += V * rows_per_it, it += V) {
+      int slot[V];
+      float2 v[V];
+#pragma unroll
+      for (int u = 0; u < V; u++) slot[u] = __ldg(pl.perm + k1 + u * rows_per_it);
+#pragma unroll
+      for (int u = 0; u < V; u++) v[u] = cmul(colp[slot[u]], cmul(twB, twc[it + u]));
+#pragma unroll
+      for (int u = 0; u < V; u++) dst[(long)(k1 + u * rows_per_it) * a.n2] = v[u];
     }
+    for (; k1 < a.n1; k1 += rows_per_it, it++)
+      dst[(long)k1 * a.n2] = cmul(colp[__ldg(pl.perm + k1)], cmul(twB, twc[it]));
   }
 }
 
@@ -177,7 +202,16 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_kernel(Pass2Args cons
     if (row >= 0) {
       float2 const *src = a.mid + (long)blk * a.nc + (long)row * a.n2;
       float2 *colp = tile + warp * a.pitch;
-      for (int n2 = lane; n2 < a.n2; n2 += 32) colp[n2] = __ldg(src + n2);
+      constexpr int U = 8;
+      int n2 = lane;
+      for (; n2 + (U - 1) * 32 < a.n2; n2 += U * 32) {
+        float2 w[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) w[u] = __ldg(src + n2 + u * 32);
+#pragma unroll
+        for (int u = 0; u < U; u++) colp[n2 + u * 32] = w[u];
+      }
+      for (; n2 < a.n2; n2 += 32) colp[n2] = __ldg(src + n2);
       __syncwarp();
       tile_fft<false>(pl, colp, lane, 32, [] { __syncwarp(); });
     }
@@ -191,8 +225,19 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_kernel(Pass2Args cons
     RowItem const it = items[i];
     if (it.kind == kRowPlain) {
       float2 const *colp = tile + i * a.pitch;
-      for (int k2 = q0; k2 < a.n2; k2 += kFwdThreads / kTile)
-        spec[(long)it.row_a + (long)a.n1 * k2] = colp[__ldg(pl.perm + k2)];
+      constexpr int V = 4, QS = kFwdThreads / kTile;
+      int k2 = q0;
+      for (; k2 + (V - 1) * QS < a.n2; k2 += V * QS) {
+        int slot[V];
+        float2 v[V];
+#pragma unroll
+        for (int u = 0; u < V; u++) slot[u] = __ldg(pl.perm + k2 + u * QS);
+#pragma unroll
+        for (int u = 0; u < V; u++) v[u] = colp[slot[u]];
+#pragma unroll
+        for (int u = 0; u < V; u++) spec[(long)it.row_a + (long)a.n1 * (k2 + u * QS)] = v[u];
+      }
+      for (; k2 < a.n2; k2 += QS) spec[(long)it.row_a + (long)a.n1 * k2] = colp[__ldg(pl.perm + k2)];
     }
     return;
   }
@@ -205,12 +250,11 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_kernel(Pass2Args cons
   float2 const *cb = (it.kind == kRowPair) ? tile + (2 * i + 1) * a.pitch : ca;
   float2 const rootC = unit_root_f(it.row_a, 2 * a.nc);  // W_N^{k1}
   int const kend = (it.kind == kRowPair) ? a.n2 : (it.kind == kRowSelf0 ? a.n2 / 2 + 1 : (a.n2 + 1) / 2);
-  for (int k2 = q0; k2 < kend; k2 += qstep) {
-    int const k2m = (it.kind == kRowSelf0) ? (k2 == 0 ? 0 : a.n2 - k2) : a.n2 - 1 - k2;
-    float2 const za = ca[__ldg(pl.perm + k2)];
-    float2 const zb = cb[__ldg(pl.perm + k2m)];
+  constexpr int V = 4;
+  auto partner = [&](int k2) { return (it.kind == kRowSelf0) ? (k2 == 0 ? 0 : a.n2 - k2) : a.n2 - 1 - k2; };
+  auto emit = [&](int k2, float2 za, float2 zb, float2 rd) {
     long const k = (long)it.row_a + (long)a.n1 * k2;
-    float2 const w = cmul(rootC, __ldg(a.rootD + k2));            // W_N^k
+    float2 const w = cmul(rootC, rd);  // W_N^k
     float2 const E = make_float2(0.5f * (za.x + zb.x), 0.5f * (za.y - zb.y));
     float2 const O = make_float2(0.5f * (za.x - zb.x), 0.5f * (za.y + zb.y));
     float2 const P = cmul(w, O);
@@ -218,7 +262,27 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_kernel(Pass2Args cons
     spec[k] = make_float2(E.x + P.y, E.y - P.x);
     long const km = a.nc - k;
     if (km != k) spec[km] = make_float2(E.x - P.y, -(E.y + P.x));
+  };
+  int k2 = q0;
+  for (; k2 + (V - 1) * qstep < kend; k2 += V * qstep) {
+    int sa[V], sb[V];
+    float2 za[V], zb[V], rd[V];
+#pragma unroll
+    for (int u = 0; u < V; u++) {
+      sa[u] = __ldg(pl.perm + k2 + u * qstep);
+      sb[u] = __ldg(pl.perm + partner(k2 + u * qstep));
+      rd[u] = __ldg(a.rootD + k2 + u * qstep);
+    }
+#pragma unroll
+    for (int u = 0; u < V; u++) {
+      za[u] = ca[sa[u]];
+      zb[u] = cb[sb[u]];
+    }
+#pragma unroll
+    for (int u = 0; u < V; u++) emit(k2 + u * qstep, za[u], zb[u], rd[u]);
   }
+  for (; k2 < kend; k2 += qstep)
+    emit(k2, ca[__ldg(pl.perm + k2)], cb[__ldg(pl.perm + partner(k2))], __ldg(a.rootD + k2));
 }
 
 // ---------------------------------------------------------------------------------------------

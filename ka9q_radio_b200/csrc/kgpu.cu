@@ -17,12 +17,19 @@
 #include "chan_kernels.cuh"
 #include "fwd_kernels.cuh"
 #include "plan.cuh"
+#include "static_kernels.cuh"
 
 using namespace kfft;
 
 // ------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
 static std::atomic<unsigned long long> g_launches{0};
+
+static std::atomic<int> g_static_on{1};  // tests can force the generic kernels
+extern "C" int kgpu_use_static_kernels(int on) {
+  g_static_on.store(on != 0);
+  return 0;
+}
 
 static int fail(char const *fmt, ...) {
   char buf[512];
@@ -46,6 +53,86 @@ static int fail(char const *fmt, ...) {
       return nullptr;                                                                    \
     }                                                                                    \
   } while (0)
+
+// ------------------------------------------------------------------ per-launch profiling -----
+// When enabled, every kernel launch is bracketed by CUDA events on the launching stream; bench.py
+// reads the per-kernel totals for its roofline line (events are markers, they do not serialise).
+enum KernelId { K_FWD_COLS = 0, K_FWD_ROWS, K_CHAN, K_NOTCH, K_RESPONSE, K_COUNT };
+static char const *const kKernelNames[K_COUNT] = {"fwd_cols", "fwd_rows", "chan", "notch", "response_fft"};
+struct ProfRec {
+  cudaEvent_t a, b;
+  int kid;
+};
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof_pending;
+static std::vector<cudaEvent_t> g_prof_pool;
+static double g_prof_ms[K_COUNT];
+static long g_prof_cnt[K_COUNT];
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) {
+    cudaEvent_t e = g_prof_pool.back();
+    g_prof_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+struct ProfScope {
+  ProfRec r;
+  cudaStream_t st;
+  bool on;
+  ProfScope(int kid, cudaStream_t s) : st(s), on(g_prof_on.load() != 0) {
+    if (!on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    r.a = prof_event();
+    r.b = prof_event();
+    r.kid = kid;
+    cudaEventRecord(r.a, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.b, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_pending.push_back(r);
+  }
+};
+static void prof_drain() {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (ProfRec &r : g_prof_pending) {
+    float ms = 0;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      g_prof_ms[r.kid] += ms;
+      g_prof_cnt[r.kid]++;
+    }
+    g_prof_pool.push_back(r.a);
+    g_prof_pool.push_back(r.b);
+  }
+  g_prof_pending.clear();
+}
+extern "C" int kgpu_profile_enable(int on) {
+  g_prof_on.store(on != 0);
+  return 0;
+}
+extern "C" int kgpu_profile_reset(void) {
+  prof_drain();
+  for (int i = 0; i < K_COUNT; i++) {
+    g_prof_ms[i] = 0;
+    g_prof_cnt[i] = 0;
+  }
+  return 0;
+}
+extern "C" int kgpu_profile_kernels(void) { return K_COUNT; }
+extern "C" const char *kgpu_profile_name(int kid) { return (kid >= 0 && kid < K_COUNT) ? kKernelNames[kid] : ""; }
+extern "C" int kgpu_profile_get(int kid, double *total_ms, long *count) {
+  if (kid < 0 || kid >= K_COUNT) return -1;
+  prof_drain();
+  if (total_ms) *total_ms = g_prof_ms[kid];
+  if (count) *count = g_prof_cnt[kid];
+  return 0;
+}
 
 extern "C" const char *kgpu_last_error(void) { return g_err.c_str(); }
 extern "C" unsigned long long kgpu_launch_count(void) { return g_launches.load(); }
@@ -198,6 +285,9 @@ struct kgpu_master {
   RowItem *d_items = nullptr;
   int n_item_ctas = 0;
   float2 *d_rootD = nullptr;
+  float2 *d_twA = nullptr, *d_twB = nullptr, *d_rootC = nullptr;  // static-kernel tables
+  int nit = 0;
+  int static_cols = 0, static_rows = 0;  // which specialised kernels apply (0 = generic)
   float2 *d_mid = nullptr;
   int mid_blocks = 0;
   size_t smem1 = 0, smem2 = 0;
@@ -276,6 +366,36 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
     CUDA_OKP(cudaMalloc(&m->d_rootD, sizeof(float2) * rootD.size()));
     CUDA_OKP(cudaMemcpy(m->d_rootD, rootD.data(), sizeof(float2) * rootD.size(), cudaMemcpyHostToDevice));
   }
+  // specialised kernels for the lengths the configured workloads use
+  {
+    TilePlan const *p1 = host_tile_plan(m->plan1), *p2 = host_tile_plan(m->plan2);
+    if (plan_is<S1296>(p1)) m->static_cols = 1296;
+    if (plan_is<S1250>(p2)) m->static_rows = 1250;
+    int const n2 = m->sp.n2;
+    m->nit = (n1 + 31) / 32;
+    std::vector<float2> tA((size_t)n2 * m->nit), tB((size_t)n2 * 32), tC((size_t)n1 / 2 + 1);
+    auto root = [](long e, long n) {
+      long double const ang = -2.0L * M_PIl * (long double)(e % n) / (long double)n;
+      return make_float2((float)cosl(ang), (float)sinl(ang));
+    };
+    for (long c = 0; c < n2; c++) {
+      for (int it = 0; it < m->nit; it++) tA[(size_t)c * m->nit + it] = root(c * 32 * it, m->nc);
+      for (int r = 0; r < 32; r++) tB[(size_t)c * 32 + r] = root(c * r, m->nc);
+    }
+    for (int k1 = 0; k1 <= n1 / 2; k1++) tC[(size_t)k1] = root(k1, 2 * m->nc);
+    CUDA_OKP(cudaMalloc(&m->d_twA, sizeof(float2) * tA.size()));
+    CUDA_OKP(cudaMalloc(&m->d_twB, sizeof(float2) * tB.size()));
+    CUDA_OKP(cudaMalloc(&m->d_rootC, sizeof(float2) * tC.size()));
+    CUDA_OKP(cudaMemcpy(m->d_twA, tA.data(), sizeof(float2) * tA.size(), cudaMemcpyHostToDevice));
+    CUDA_OKP(cudaMemcpy(m->d_twB, tB.data(), sizeof(float2) * tB.size(), cudaMemcpyHostToDevice));
+    CUDA_OKP(cudaMemcpy(m->d_rootC, tC.data(), sizeof(float2) * tC.size(), cudaMemcpyHostToDevice));
+    size_t const s1 = sizeof(float2) * (size_t)kTile * m->pitch1, s2 = sizeof(float2) * (size_t)kTile * m->pitch2;
+    if (set_smem((const void *)fwd_cols_static<0, S1296>, s1) || set_smem((const void *)fwd_cols_static<1, S1296>, s1) ||
+        set_smem((const void *)fwd_rows_static<S1250, true>, s2) || set_smem((const void *)fwd_rows_static<S1250, false>, s2)) {
+      kgpu_master_destroy(m);
+      return nullptr;
+    }
+  }
   if (set_smem((const void *)fwd_cols_kernel<0>, m->smem1) || set_smem((const void *)fwd_cols_kernel<1>, m->smem1) ||
       set_smem((const void *)fwd_rows_kernel, m->smem2)) {
     kgpu_master_destroy(m);
@@ -288,6 +408,9 @@ extern "C" void kgpu_master_destroy(kgpu_master *m) {
   if (!m) return;
   cudaFree(m->d_items);
   cudaFree(m->d_rootD);
+  cudaFree(m->d_twA);
+  cudaFree(m->d_twB);
+  cudaFree(m->d_rootC);
   cudaFree(m->d_mid);
   cudaFree(m->d_notch);
   delete m;
@@ -340,10 +463,25 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
   a1.stats = (fmt == KGPU_FMT_I16) ? (IngestStats *)d_stats : nullptr;
   if (a1.stats) CUDA_OK(cudaMemsetAsync(d_stats, 0, sizeof(IngestStats) * (size_t)nblocks, st));
   dim3 const g1((unsigned)((m->sp.n2 + kTile - 1) / kTile), (unsigned)nblocks);
-  if (fmt == KGPU_FMT_I16)
-    fwd_cols_kernel<1><<<g1, kFwdThreads, m->smem1, st>>>(a1);
-  else
-    fwd_cols_kernel<0><<<g1, kFwdThreads, m->smem1, st>>>(a1);
+  FwdTables tb;
+  tb.twA = m->d_twA;
+  tb.twB = m->d_twB;
+  tb.rootC = m->d_rootC;
+  tb.nit = m->nit;
+  bool const use_static = g_static_on.load() != 0;
+  {
+    ProfScope ps(K_FWD_COLS, st);
+    size_t const s1 = sizeof(float2) * (size_t)kTile * m->pitch1;
+    if (use_static && m->static_cols == 1296) {
+      if (fmt == KGPU_FMT_I16)
+        fwd_cols_static<1, S1296><<<g1, kFwdThreads, s1, st>>>(a1, tb);
+      else
+        fwd_cols_static<0, S1296><<<g1, kFwdThreads, s1, st>>>(a1, tb);
+    } else if (fmt == KGPU_FMT_I16)
+      fwd_cols_kernel<1><<<g1, kFwdThreads, m->smem1, st>>>(a1);
+    else
+      fwd_cols_kernel<0><<<g1, kFwdThreads, m->smem1, st>>>(a1);
+  }
   g_launches++;
   Pass2Args a2;
   a2.mid = m->d_mid;
@@ -358,7 +496,16 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
   a2.spec = (float2 *)d_spec;
   a2.spec_stride = m->spec_stride;
   dim3 const g2((unsigned)m->n_item_ctas, (unsigned)nblocks);
-  fwd_rows_kernel<<<g2, kFwdThreads, m->smem2, st>>>(a2);
+  {
+    ProfScope ps(K_FWD_ROWS, st);
+    if (use_static && m->static_rows == 1250) {
+      if (a2.real_split)
+        fwd_rows_static<S1250, true><<<g2, kFwdThreads, m->smem2, st>>>(a2, tb);
+      else
+        fwd_rows_static<S1250, false><<<g2, kFwdThreads, m->smem2, st>>>(a2, tb);
+    } else
+      fwd_rows_kernel<<<g2, kFwdThreads, m->smem2, st>>>(a2);
+  }
   g_launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -386,8 +533,11 @@ extern "C" int kgpu_master_set_notches(kgpu_master *m, int const *bins, double c
 extern "C" int kgpu_apply_notches(kgpu_master *m, void *d_spec, int nblocks, void *stream) {
   if (!m || !d_spec) return fail("kgpu_apply_notches: bad arguments");
   if (m->n_notch == 0) return 0;
-  notch_kernel<<<1, 32 * ((m->n_notch + 31) / 32), 0, (cudaStream_t)stream>>>(
-      m->d_notch, m->n_notch, m->notch_sequential, (float2 *)d_spec, m->spec_stride, nblocks);
+  {
+    ProfScope ps(K_NOTCH, (cudaStream_t)stream);
+    notch_kernel<<<1, 32 * ((m->n_notch + 31) / 32), 0, (cudaStream_t)stream>>>(
+        m->d_notch, m->n_notch, m->notch_sequential, (float2 *)d_spec, m->spec_stride, nblocks);
+  }
   g_launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -487,6 +637,11 @@ struct kgpu_bank {
   long out_stride = 0;
   bool dirty = true;
   int max_points = 0;
+  struct Group {
+    int plan, points, off, count;
+  };
+  std::vector<Group> groups;  // enabled channels grouped by inverse-transform plan
+  int *d_order = nullptr;
 };
 
 static void resolve_walk(kgpu_master const *m, ChanHost const &c, ChanDesc &d) {
@@ -558,7 +713,24 @@ static int bank_commit(kgpu_bank *b, cudaStream_t st) {
     }
   }
   b->out_stride = (off + 3) / 4 * 4;
+  // one launch per distinct plan: order[] lists that plan's descriptors
+  std::vector<int> order;
+  b->groups.clear();
+  for (int i = 0; i < b->nchan; i++) {
+    if (b->desc[(size_t)i].plan < 0) continue;
+    bool found = false;
+    for (auto &g : b->groups)
+      if (g.plan == b->desc[(size_t)i].plan) found = true;
+    if (found) continue;
+    kgpu_bank::Group g{b->desc[(size_t)i].plan, b->desc[(size_t)i].points, (int)order.size(), 0};
+    for (int k = i; k < b->nchan; k++)
+      if (b->desc[(size_t)k].plan == g.plan) order.push_back(k);
+    g.count = (int)order.size() - g.off;
+    b->groups.push_back(g);
+  }
   CUDA_OK(cudaStreamSynchronize(st));
+  if (!order.empty())
+    CUDA_OK(cudaMemcpy(b->d_order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(b->d_desc, b->desc.data(), sizeof(ChanDesc) * b->desc.size(), cudaMemcpyHostToDevice));
   b->dirty = false;
   return 0;
@@ -574,12 +746,14 @@ extern "C" kgpu_bank *kgpu_bank_create(kgpu_master *m, int capacity) {
   b->capacity = capacity;
   b->ch.resize((size_t)capacity);
   CUDA_OKP(cudaMalloc(&b->d_desc, sizeof(ChanDesc) * (size_t)capacity));
+  CUDA_OKP(cudaMalloc(&b->d_order, sizeof(int) * (size_t)capacity));
   return b;
 }
 extern "C" void kgpu_bank_destroy(kgpu_bank *b) {
   if (!b) return;
   cudaFree(b->d_resp);
   cudaFree(b->d_desc);
+  cudaFree(b->d_order);
   delete b;
 }
 static bool bad_idx(kgpu_bank const *b, int idx) { return !b || idx < 0 || idx >= b->capacity; }
@@ -693,26 +867,46 @@ extern "C" long kgpu_bank_out_offset(kgpu_bank const *b, int idx) {
   return idx < b->nchan ? b->out_off[(size_t)idx] : -1;
 }
 
-static int launch_chan(kgpu_bank *b, const void *d_spec, int nblocks, void *d_out, long out_stride, int base, int n,
-                       cudaStream_t st) {
+template <class P> static int launch_chan_static(ChanArgs const &a, int n, int nblocks, cudaStream_t st) {
+  size_t const sm = sizeof(float2) * (size_t)(2 * P::len + 4) * kChanWarps;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (set_smem((const void *)chan_static<P>, sm)) return -1;
+    attr_done = true;
+  }
+  dim3 const g((unsigned)((n + kChanWarps - 1) / kChanWarps), (unsigned)nblocks);
+  chan_static<P><<<g, kChanWarps * 32, sm, st>>>(a);
+  return 0;
+}
+
+// one (plan, descriptor list) launch
+static int launch_chan(kgpu_bank *b, const void *d_spec, int nblocks, void *d_out, long out_stride, int plan,
+                       int points, int const *d_order, int base, int n, cudaStream_t st) {
   ChanArgs a;
   a.spec = (float2 const *)d_spec;
   a.spec_stride = b->m->spec_stride;
   a.m_bins = b->m->bins;
   a.wrap = (b->m->in_type == KGPU_COMPLEX);
   a.desc = b->d_desc;
-  a.nchan = n;
+  a.order = d_order;
+  a.norder = n;
   a.chan_base = base;
   a.resp = b->d_resp;
   a.out = (float2 *)d_out;
   a.out_stride = out_stride;
-  a.pitch = (b->max_points + 3) / 4 * 4 + 2;
+  a.pitch = (points + 3) / 4 * 4 + 2;
+  ProfScope ps(K_CHAN, st);
+  g_launches++;
+  TilePlan const *tp = host_tile_plan(plan);
+  if (g_static_on.load()) {
+    if (plan_is<S600>(tp)) return launch_chan_static<S600>(a, n, nblocks, st);
+    if (plan_is<S300>(tp)) return launch_chan_static<S300>(a, n, nblocks, st);
+    if (plan_is<S1200>(tp)) return launch_chan_static<S1200>(a, n, nblocks, st);
+  }
   size_t const sm = sizeof(float2) * (size_t)a.pitch * kChanWarps;
   if (set_smem((const void *)chan_kernel, sm)) return -1;
   dim3 const g((unsigned)((n + kChanWarps - 1) / kChanWarps), (unsigned)nblocks);
   chan_kernel<<<g, kChanWarps * 32, sm, st>>>(a);
-  g_launches++;
-  CUDA_OK(cudaGetLastError());
   return 0;
 }
 
@@ -720,16 +914,28 @@ extern "C" int kgpu_bank_run(kgpu_bank *b, const void *d_spec, int nblocks, void
   if (!b || !d_spec || !d_out || nblocks < 1) return fail("kgpu_bank_run: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   if (bank_commit(b, st)) return -1;
-  if (b->nchan == 0) return 0;
-  return launch_chan(b, d_spec, nblocks, d_out, b->out_stride, 0, b->nchan, st);
+  for (auto const &g : b->groups)
+    if (launch_chan(b, d_spec, nblocks, d_out, b->out_stride, g.plan, g.points, b->d_order + g.off, 0, g.count, st))
+      return -1;
+  CUDA_OK(cudaGetLastError());
+  return 0;
 }
 extern "C" int kgpu_bank_run_one(kgpu_bank *b, int idx, const void *d_spec, void *d_out, void *stream) {
   if (bad_idx(b, idx) || !d_spec || !d_out) return fail("kgpu_bank_run_one: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   if (bank_commit(b, st)) return -1;
+  ChanHost const &c = b->ch[(size_t)idx];
+  if (!c.defined || !c.has_response || !c.enabled) return fail("kgpu_bank_run_one: channel %d not runnable", idx);
   // write this channel's olen samples at d_out[0..olen): shift the row origin back by out_off
   float2 *origin = (float2 *)d_out - b->out_off[(size_t)idx];
-  return launch_chan(b, d_spec, 1, origin, 0, idx, 1, st);
+  if (launch_chan(b, d_spec, 1, origin, 0, c.plan, c.points, nullptr, idx, 1, st)) return -1;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+/* make the descriptor table current now (e.g. before reading out_stride) and order it after `stream` */
+extern "C" int kgpu_bank_commit(kgpu_bank *b, void *stream) {
+  if (!b) return fail("kgpu_bank_commit: bad arguments");
+  return bank_commit(b, (cudaStream_t)stream);
 }
 
 // pure host helpers (usable without a GPU): what the planner would pick

@@ -119,9 +119,13 @@ def test_forward_linearity_and_impulse(oracle, cuda_dev):
     cz.close()
 
 
-def test_forward_full_size_vs_oracle(oracle, cuda_dev):
-    """cfg-2 geometry (N = 3 240 000), one block of int16 tones+noise, against the CPU oracle."""
+@pytest.mark.parametrize("static", [1, 0])
+def test_forward_full_size_vs_oracle(oracle, cuda_dev, static):
+    """cfg-2 geometry (N = 3 240 000), one block of int16 tones+noise, against the CPU oracle;
+    once through the compile-time specialised kernels, once through the generic ones."""
     from ka9q_radio_b200 import capi
+
+    capi.load().kgpu_use_static_kernels(static)
 
     L, M = 2592000, 648001
     fs = 129.6e6
@@ -142,6 +146,7 @@ def test_forward_full_size_vs_oracle(oracle, cuda_dev):
     e_ora = np.sqrt(np.mean(np.abs(ref - truth) ** 2))
     assert e_gpu < 2.0 * e_ora
     cz.close()
+    capi.load().kgpu_use_static_kernels(1)
 
 
 def test_notches(oracle, cuda_dev):
@@ -214,16 +219,20 @@ def _chan_case(oracle, cuda_dev, in_type, L, M, chans, nb=3, seed=1):
     return worst
 
 
-def test_channels_real_master_all_sizes(oracle, cuda_dev):
+@pytest.mark.parametrize("static", [1, 0])
+def test_channels_real_master_all_sizes(oracle, cuda_dev, static):
     from ka9q_radio_b200 import capi
 
+    capi.load().kgpu_use_static_kernels(static)
     L, M = 48000, 12001
     chans = []
     for olen in (240, 480, 960, 120, 160):
         for shift in (7380, -7380, 0, 3, 29990, -29990, 30010, 120, -50):
             chans.append(dict(olen=olen, shift=shift, low=-0.3, high=0.35, beta=11.0))
     chans.append(dict(olen=480, shift=7383, low=-0.2, high=0.2, beta=5.0, isb=True))
-    assert _chan_case(oracle, cuda_dev, capi.KGPU_REAL, L, M, chans) < TOL
+    worst = _chan_case(oracle, cuda_dev, capi.KGPU_REAL, L, M, chans)
+    capi.load().kgpu_use_static_kernels(1)
+    assert worst < TOL
 
 
 def test_channels_complex_master_wrap(oracle, cuda_dev):
@@ -231,7 +240,7 @@ def test_channels_complex_master_wrap(oracle, cuda_dev):
 
     L, M = 4000, 1001  # N = 5000
     chans = []
-    for olen in (80, 160, 40):
+    for olen in (80, 160, 40, 480):  # 480 -> 600 points: the specialised kernel's wrap path
         for shift in (615, -615, 0, 2499, -2499, 2450, -2480, 2490, -2500, 1, -1):
             chans.append(dict(olen=olen, shift=shift, low=-0.3, high=0.35, beta=11.0))
     chans.append(dict(olen=80, shift=600, low=-0.2, high=0.2, beta=5.0, isb=True))
