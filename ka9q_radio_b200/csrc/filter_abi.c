@@ -110,9 +110,9 @@ static void *ring_alloc(size_t size) {
     return NULL;
   }
   memset(base, 0, size);
-  /* pin both views so the per-block H2D is a true async DMA; harmless if the driver refuses */
-  if (cudaHostRegister(base, size, cudaHostRegisterPortable) != cudaSuccess ||
-      cudaHostRegister(base + size, size, cudaHostRegisterPortable) != cudaSuccess)
+  /* pin the primary view so the per-block H2D is a true async DMA (the copy never reads through
+   * the mirror view, see window_h2d); harmless if the driver refuses */
+  if (cudaHostRegister(base, size, cudaHostRegisterPortable) != cudaSuccess)
     (void)cudaGetLastError();
   return base;
 }
@@ -121,9 +121,25 @@ static void ring_free(void *base, size_t size) {
     return;
   if (cudaHostUnregister(base) != cudaSuccess)
     (void)cudaGetLastError();
-  if (cudaHostUnregister((char *)base + size) != cudaSuccess)
-    (void)cudaGetLastError();
   munmap(base, 2 * size);
+}
+
+static int kgf_fail(char const *where) {
+  fprintf(stderr, "ka9q-gpu filter: %s failed: kgpu: \"%s\" cuda: %s\n", where, kgpu_last_error(),
+          cudaGetErrorString(cudaGetLastError()));
+  return -1;
+}
+
+/* H2D of one FFT window that starts inside the primary view and may run past its end: the part
+ * beyond the end is the start of the ring again (that is what the mirror view shows the CPU). */
+static int window_h2d(void *dst, void const *src, size_t bytes, void const *ring, size_t ring_size, cudaStream_t st) {
+  char const *end = (char const *)ring + ring_size;
+  if ((char const *)src + bytes <= end)
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st) == cudaSuccess ? 0 : -1;
+  size_t const first = (size_t)(end - (char const *)src);
+  if (cudaMemcpyAsync(dst, src, first, cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return -1;
+  return cudaMemcpyAsync((char *)dst + first, ring, bytes - first, cudaMemcpyHostToDevice, st) == cudaSuccess ? 0 : -1;
 }
 
 static void *cache_aligned(size_t bytes) {
@@ -417,10 +433,11 @@ int execute_filter_input(struct filter_in *const f) {
     kgf_ring_wrap((void **)&f->input_read_pointer.r, f->input_buffer, f->input_buffer_size);
   }
   float complex *spec = c->d_spec + (size_t)slot * (size_t)c->spec_stride;
-  if (cudaMemcpyAsync(c->d_win[slot], src, bytes, cudaMemcpyHostToDevice, c->st) != cudaSuccess)
-    rc = -1;
+  if (window_h2d(c->d_win[slot], src, bytes, c->i16_mode ? c->i16_ring : f->input_buffer,
+                 c->i16_mode ? c->i16_ring_size : f->input_buffer_size, c->st) != 0)
+    rc = kgf_fail("execute_filter_input: H2D of the window");
   if (rc == 0 && kgpu_forward(c->km, c->d_win[slot], fmt, scale, c->i16_derand, 1, spec, NULL, c->st) != 0)
-    rc = -1;
+    rc = kgf_fail("execute_filter_input: kgpu_forward");
   if (rc == 0 && f->notches)
     kgpu_apply_notches(c->km, spec, 1, c->st);
   /* every slave, batched, with the shift it used last (radio.c:1491: shifts move only on retune) */
@@ -513,7 +530,7 @@ int execute_filter_output(struct filter_out *const slave, int const shift) {
   pthread_mutex_unlock(&master->filter_mutex);
 
   if (cudaEventSynchronize(c->done[slot]) != cudaSuccess)
-    return -1;
+    return kgf_fail("execute_filter_output: waiting for the block");
   if (slave->out_type == SPECTRUM)
     return 0; /* the caller reads master->fdomain[] itself (filter.c:368-371, spectrum.c:318) */
   struct slave_ctx *sc = (struct slave_ctx *)slave->rev_plan;
@@ -540,11 +557,14 @@ int execute_filter_output(struct filter_out *const slave, int const shift) {
     kgpu_bank_set_shift(c->bank, i, shift);
     kgpu_bank_set_flags(c->bank, i, slave->isb ? KGPU_CHAN_ISB : 0);
     float complex const *spec = c->d_spec + (size_t)slot * (size_t)c->spec_stride;
-    if (ensure_one(c, slave->olen) != 0 || kgpu_bank_run_one(c->bank, i, spec, c->d_one, c->st_one) != 0 ||
-        cudaMemcpyAsync(c->h_one, c->d_one, sizeof(float complex) * (size_t)slave->olen, cudaMemcpyDeviceToHost,
-                        c->st_one) != cudaSuccess ||
-        cudaStreamSynchronize(c->st_one) != cudaSuccess)
-      rc = -1;
+    if (ensure_one(c, slave->olen) != 0)
+      rc = kgf_fail("execute_filter_output: scratch allocation");
+    else if (kgpu_bank_run_one(c->bank, i, spec, c->d_one, c->st_one) != 0)
+      rc = kgf_fail("execute_filter_output: kgpu_bank_run_one");
+    else if (cudaMemcpyAsync(c->h_one, c->d_one, sizeof(float complex) * (size_t)slave->olen, cudaMemcpyDeviceToHost,
+                             c->st_one) != cudaSuccess ||
+             cudaStreamSynchronize(c->st_one) != cudaSuccess)
+      rc = kgf_fail("execute_filter_output: D2H of the recomputed channel");
     else
       memcpy(slave->output.c, c->h_one, sizeof(float complex) * (size_t)slave->olen);
   }

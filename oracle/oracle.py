@@ -212,14 +212,9 @@ def ref_available() -> bool:
     return (HERE / "_ref/libka9qref.so").exists()
 
 
-def ref_lib() -> C.CDLL:
-    global _ref
-    if _ref is None:
-        build()
-        p = HERE / "_ref/libka9qref.so"
-        if not p.exists():
-            raise FileNotFoundError("oracle/_ref/libka9qref.so not built (needs /root/reference)")
-        R = C.CDLL(str(p))
+def bind_driver(R: C.CDLL) -> C.CDLL:
+    """ctypes prototypes of the flat filter.h driver API (oracle/ref_driver.c, tests/abi/filter_driver.c)."""
+    if True:
         R.ref_open.restype = C.c_void_p
         R.ref_open.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
         R.ref_close.argtypes = [C.c_void_p]
@@ -236,6 +231,17 @@ def ref_lib() -> C.CDLL:
         R.ref_execute_channel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         R.ref_channel_drops.argtypes = [C.c_void_p, C.c_int]
         R.ref_channel_drops.restype = C.c_uint
+    return R
+
+
+def ref_lib() -> C.CDLL:
+    global _ref
+    if _ref is None:
+        build()
+        p = HERE / "_ref/libka9qref.so"
+        if not p.exists():
+            raise FileNotFoundError("oracle/_ref/libka9qref.so not built (needs /root/reference)")
+        R = bind_driver(C.CDLL(str(p)))
         R.ref_siggen_real.argtypes = [_f32p, C.c_long, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
         R.ref_siggen_real.restype = None
         R.ref_siggen_complex.argtypes = [_c64p, C.c_long, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
@@ -250,8 +256,8 @@ def ref_lib() -> C.CDLL:
 class RefSession:
     """The reference's own create_filter_input/output + execute path, inline forward FFT."""
 
-    def __init__(self, L, M, in_type, nworkers=0):
-        self.R = ref_lib()
+    def __init__(self, L, M, in_type, nworkers=0, lib=None):
+        self.R = lib if lib is not None else ref_lib()
         self.h = self.R.ref_open(L, M, in_type, nworkers)
         if not self.h:
             raise RuntimeError("create_filter_input failed")
@@ -319,12 +325,13 @@ class RefSession:
         self.close()
 
 
-def ref_run_stream(stream, L, M, channels, notch_bins=None, keep_spectra=False):
-    """Same contract as run_stream() but executed by the reference's own filter.c."""
+def ref_run_stream(stream, L, M, channels, notch_bins=None, keep_spectra=False, lib=None):
+    """Same contract as run_stream() but executed by the reference's own filter.c (or, with
+    lib=<tests/abi driver>, by whatever library implements the filter.h surface)."""
     in_type = KO_COMPLEX if np.iscomplexobj(stream) else KO_REAL
     nblocks = len(stream) // L
     outs, spectra = [], []
-    with RefSession(L, M, in_type) as s:
+    with RefSession(L, M, in_type, lib=lib) as s:
         if notch_bins is not None:
             s.set_notches(list(notch_bins))
         ids = [s.add_channel(ch["olen"], ch["low"], ch["high"], ch["beta"]) for ch in channels]

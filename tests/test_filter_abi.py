@@ -1,0 +1,166 @@
+"""The reference-facing surface: libka9qgpu.so behind ka9q-radio's filter.h.
+
+CPU part: struct layouts of include/ka9q_gpu_filter.h equal the reference's own src/filter.h
+(offset report produced by the same C driver compiled against either header).
+GPU part: the driver exercises create_filter_input/output, write_*filter, set_filter,
+execute_filter_output exactly as radiod does and is compared with the oracle; the variant of
+the driver compiled against the REFERENCE header proves the untouched sources bind unchanged.
+"""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+BUILD = ROOT / "tests" / "abi" / "_build"
+TOL = 1e-5
+
+
+def _build():
+    subprocess.run(["make", "-C", str(ROOT / "tests" / "abi"), "-s"], check=True)
+
+
+def _load(name):
+    _build()
+    p = BUILD / name
+    if not p.exists():
+        return None
+    from oracle import oracle as O
+
+    lib = O.bind_driver(C.CDLL(str(p)))
+    lib.ref_layout_report.argtypes = [C.c_char_p, C.c_int]
+    lib.ref_write_real_inplace.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"), C.c_int]
+    lib.ref_channel_sample_index.argtypes = [C.c_void_p, C.c_int]
+    lib.ref_channel_sample_index.restype = C.c_ulonglong
+    lib.ref_threaded_run.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS"), C.c_int,
+                                     C.c_void_p, C.c_void_p]
+    if hasattr(lib, "ref_write_i16"):
+        lib.ref_write_i16.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(np.int16, flags="C_CONTIGUOUS"), C.c_int, C.c_float, C.c_int]
+    return lib
+
+
+def _report(lib):
+    buf = C.create_string_buffer(8192)
+    lib.ref_layout_report(buf, 8192)
+    return buf.value.decode()
+
+
+def test_struct_layout_matches_reference_header():
+    ours = _load("driver_gpuhdr.so")
+    ref = _load("driver_refhdr.so")
+    if ref is None:
+        pytest.skip("driver_refhdr.so not built (needs /root/reference at build time)")
+    assert _report(ours) == _report(ref)
+    assert "filter_in.fdomain" in _report(ours)
+
+
+# ------------------------------------------------------------------ GPU behaviour ---------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("driver", ["driver_gpuhdr.so", "driver_refhdr.so"])
+def test_radiod_style_flow_matches_oracle(oracle, cuda_dev, driver):
+    lib = _load(driver)
+    if lib is None:
+        pytest.skip(f"{driver} not built")
+    L, M = 48000, 12001
+    x = oracle.siggen_real(5 * L, 10 ** (-20 / 20), 10 ** (-40 / 20), 0.25, 10 ** (3 / 20))
+    chans = [dict(olen=480, shift=15000, low=-1 / 3, high=1 / 3, beta=11.0),
+             dict(olen=480, shift=-15000, low=-1 / 3, high=1 / 3, beta=11.0),
+             dict(olen=240, shift=14990, low=0.01, high=0.25, beta=11.0),
+             dict(olen=960, shift=15010, low=-0.2, high=0.2, beta=7.0, isb=True)]
+    got, gspec = oracle.ref_run_stream(x, L, M, chans, notch_bins=[77], keep_spectra=True, lib=lib)
+    ref, rspec = oracle.run_stream(x, L, M, chans, notch_bins=[77], keep_spectra=True)
+    for b in range(5):
+        assert np.abs(gspec[b] - rspec[b]).max() / np.abs(rspec[b]).max() < TOL   # master->fdomain[] on the host
+        for c in range(len(chans)):
+            assert np.abs(got[b][c] - ref[b][c]).max() / np.abs(ref[b][c]).max() < TOL, (b, c)
+
+
+@pytest.mark.gpu
+def test_retune_filter_change_and_bookkeeping(oracle, cuda_dev):
+    """Shift and filter changes between blocks take the recompute path and then rejoin the batch;
+    sample_index, block_drops and the no-response / lap semantics follow filter.c."""
+    lib = _load("driver_gpuhdr.so")
+    L, M = 4800, 1201
+    N = L + M - 1
+    nb = 8
+    x = oracle.siggen_real(nb * L, 0.1, 0.02, 0.31, 1.0)
+    with oracle.RefSession(L, M, oracle.KO_REAL, lib=lib) as s:
+        a = s.add_channel(48, -0.3, 0.3, 9.0)
+        b = s.add_channel(96, -0.2, 0.4, 5.0)
+        shifts_a = [1800, 1800, 1801, 1801, -1801, -1801, 1800, 1800]
+        for blk in range(nb):
+            if blk == 4:
+                lib.ref_retune_channel(s.h, b, -0.1, 0.1, 11.0)
+            assert lib.ref_write_real_inplace(s.h, x[blk * L:(blk + 1) * L], L) == 1
+            ya = s.execute(a, shifts_a[blk])
+            yb = s.execute(b, 1700)
+            assert lib.ref_channel_sample_index(s.h, a) == blk * L
+            X = oracle.forward(oracle.block_window(x, L, M, blk))
+            Ra = oracle.design_response(60, 48, N, True, -0.3, 0.3, 9.0)
+            Rb = oracle.design_response(120, 96, N, True, *((-0.2, 0.4, 5.0) if blk < 4 else (-0.1, 0.1, 11.0)))
+            ra = oracle.channel_block(oracle.KO_REAL, X, Ra, shifts_a[blk])[-48:]
+            rb = oracle.channel_block(oracle.KO_REAL, X, Rb, 1700)[-96:]
+            assert np.abs(ya - ra).max() / np.abs(ra).max() < TOL, blk
+            assert np.abs(yb - rb).max() / np.abs(rb).max() < TOL, blk
+        assert lib.ref_channel_drops(s.h, a) == 0
+
+
+@pytest.mark.gpu
+def test_channel_threads_like_radiod(oracle, cuda_dev):
+    """One pthread per channel blocking in execute_filter_output while a producer writes through
+    the ring pointer (radio.c:996,1460; rx888.c:800-826): no drops, outputs equal the oracle."""
+    lib = _load("driver_gpuhdr.so")
+    L, M, nb, nch = 48000, 12001, 6, 48
+    x = oracle.siggen_real(nb * L, 0.1, 0.02, 0.2, 1.0)
+    chans = [dict(olen=480, shift=9000 + 400 * i, low=-1 / 3, high=1 / 3, beta=11.0) for i in range(nch)]
+    with oracle.RefSession(L, M, oracle.KO_REAL, lib=lib) as s:
+        for ch in chans:
+            s.add_channel(ch["olen"], ch["low"], ch["high"], ch["beta"])
+        outs = [np.zeros(nb * 480, np.complex64) for _ in range(nch)]
+        ptrs = (C.c_void_p * nch)(*[o.ctypes.data for o in outs])
+        shifts = (C.c_int * nch)(*[ch["shift"] for ch in chans])
+        drops = lib.ref_threaded_run(s.h, x, nb, C.cast(shifts, C.c_void_p), C.cast(ptrs, C.c_void_p))
+    assert drops == 0
+    ref, _ = oracle.run_stream(x, L, M, chans)
+    for c in range(nch):
+        for b in range(nb):
+            r = ref[b][c]
+            assert np.abs(outs[c][b * 480:(b + 1) * 480] - r).max() / np.abs(r).max() < TOL, (c, b)
+
+
+@pytest.mark.gpu
+def test_write_i16filter_extension(oracle, cuda_dev):
+    lib = _load("driver_gpuhdr.so")
+    L, M, nb = 48000, 12001, 3
+    f = [0.25, 0.1]
+    xi = oracle.siggen_tones_i16(nb * L, f, [0.1, 0.05], 0.01, 1)
+    scale = np.float32(10 ** (3 / 20) / 32768)
+    xf, _, _ = oracle.convert_i16(xi, scale)
+    ch = dict(olen=480, shift=15000, low=-1 / 3, high=1 / 3, beta=11.0)
+    ref, _ = oracle.run_stream(xf, L, M, [ch])
+    with oracle.RefSession(L, M, oracle.KO_REAL, lib=lib) as s:
+        c = s.add_channel(480, -1 / 3, 1 / 3, 11.0)
+        for b in range(nb):
+            # ragged writes, as USB transfers would deliver them
+            blk = xi[b * L:(b + 1) * L]
+            fired = 0
+            for lo, hi in ((0, 16384), (16384, 40000), (40000, L)):
+                fired += lib.ref_write_i16(s.h, np.ascontiguousarray(blk[lo:hi]), hi - lo, float(scale), 0)
+            assert fired == 1
+            y = s.execute(c, 15000)
+            assert np.abs(y - ref[b][0]).max() / np.abs(ref[b][0]).max() < TOL
+
+
+@pytest.mark.gpu
+def test_error_conventions(oracle, cuda_dev):
+    lib = _load("driver_gpuhdr.so")
+    assert not lib.ref_open(0, 5, oracle.KO_REAL, 0)            # L <= 0
+    assert not lib.ref_open(4801, 1201, oracle.KO_REAL, 0)      # odd L for a REAL master: unsupported, -1
+    s = oracle.RefSession(4800, 1201, oracle.KO_REAL, lib=lib)
+    with pytest.raises(RuntimeError):
+        s.add_channel(47, -0.3, 0.3, 5.0)                        # 47*6000 % 4800 != 0 (filter.c:312-316)
+    with pytest.raises(RuntimeError):
+        s.add_channel(48, -0.3, 0.3, 5.0, out_type=oracle.KO_REAL)   # REAL output not served
+    s.close()
