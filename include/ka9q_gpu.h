@@ -111,6 +111,15 @@ int kgpu_bank_commit(kgpu_bank *b, void *stream);
  * kernel exists (both are parity-tested). Default 1. */
 int kgpu_use_static_kernels(int on);
 
+/* Experiment knobs for A/B measurements (0 = shipped default). key 0/1: butterflies in flight per
+ * lane in the cols/rows kernels (1 or 2). */
+int kgpu_set_tuning(int key, int value);
+
+/* Diagnostics: device buffer (6 uint64 per CTA of the cols kernel) receiving globaltimer stamps
+ * at the phase boundaries; NULL (default) disables. */
+int kgpu_set_debug_buffer(void *d_buf);
+int kgpu_set_debug_buffer_rows(void *d_buf); /* same for the rows kernel */
+
 /* Planner introspection, pure host code (works without a GPU): the in-register radices chosen for
  * a column transform of length len (returns their count, -1 if unplannable) and the two-pass split
  * n = n1*n2 of a long transform. */

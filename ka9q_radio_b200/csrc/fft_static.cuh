@@ -48,44 +48,112 @@ template <class P> struct SlotOf<P, P::nst> {
 };
 template <class P> __device__ __forceinline__ int static_slot(int k) { return SlotOf<P>::run(k); }
 
-template <class P, bool INV, int I>
+// number of stage-twiddle entries of plan P (same layout as the registry table)
+template <class P> constexpr int static_tw_count() { return P::tw_off(P::nst); }
+
+// streaming global load that does not displace the L1-resident tables
+__device__ __forceinline__ int ldg_stream_b32(int const *p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float2 ldg_stream_f2(float2 const *p) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+
+// One butterfly of stage I at butterfly index u: load / transform / twiddle / store helpers.
+template <class P, int I> struct StageGeom {
+  static constexpr int R = P::rad(I), NSUB = P::nsub(I), S = P::stride(I), NB = P::len / R;
+  static __device__ __forceinline__ void split(int u, int &b, int &j) {
+    if (S == 1) {
+      b = u;
+      j = 0;
+    } else {
+      b = u / S;
+      j = u - b * S;
+    }
+  }
+};
+
+// TWS: the twiddle table pointer is in shared memory (plain loads) instead of global (__ldg).
+// ILP: butterflies of consecutive loop iterations handled together (loads of all first, then the
+// arithmetic, then the stores) so one warp keeps ILP independent chains in flight.
+template <class P, bool INV, int I, bool TWS, int ILP, int NL = 32>
 __device__ __forceinline__ void static_stage(float2 *__restrict__ col, float2 const *__restrict__ tw, int lane) {
-  constexpr int R = P::rad(I), NSUB = P::nsub(I), S = P::stride(I), NB = P::len / R;
-  constexpr int ITERS = (NB + 31) / 32;
+  using G = StageGeom<P, I>;
+  constexpr int R = G::R, NSUB = G::NSUB, S = G::S, NB = G::NB;
+  constexpr int ITERS = (NB + NL - 1) / NL;
   float2 const *twi = tw + P::tw_off(I);
 #pragma unroll
-  for (int it = 0; it < ITERS; it++) {
-    int const u = lane + 32 * it;
-    if ((NB % 32 == 0) || it + 1 < ITERS || u < NB) {
-      int const b = (S == 1) ? u : u / S;
-      int const j = (S == 1) ? 0 : u - b * S;
-      float2 *p = col + b * NSUB + j;
-      float2 x[R];
+  for (int it0 = 0; it0 < ITERS; it0 += ILP) {
+    float2 x[ILP][R];
+    float2 *p[ILP];
+    int jj[ILP];
+    bool ok[ILP];
 #pragma unroll
-      for (int m = 0; m < R; m++) x[m] = p[m * S];
-      Dft<R, INV>::run(x);
-      if (S > 1) {
+    for (int q = 0; q < ILP; q++) {
+      int const u = lane + NL * (it0 + q);
+      ok[q] = (it0 + q < ITERS) && ((NB % NL == 0) || it0 + q + 1 < ITERS || u < NB);
+      int b, j;
+      G::split(ok[q] ? u : 0, b, j);
+      jj[q] = j;
+      p[q] = col + b * NSUB + j;
+      if (ok[q]) {
 #pragma unroll
-        for (int t = 1; t < R; t++) {
-          float2 const w = __ldg(twi + (t - 1) * S + j);
-          x[t] = INV ? cmulc(x[t], w) : cmul(x[t], w);
+        for (int m = 0; m < R; m++) x[q][m] = p[q][m * S];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < ILP; q++) {
+      if (ok[q]) {
+        Dft<R, INV>::run(x[q]);
+        if (S > 1) {
+#pragma unroll
+          for (int t = 1; t < R; t++) {
+            float2 const w = TWS ? twi[(t - 1) * S + jj[q]] : __ldg(twi + (t - 1) * S + jj[q]);
+            x[q][t] = INV ? cmulc(x[q][t], w) : cmul(x[q][t], w);
+          }
         }
       }
+    }
 #pragma unroll
-      for (int t = 0; t < R; t++) p[t * S] = x[t];
+    for (int q = 0; q < ILP; q++) {
+      if (ok[q]) {
+#pragma unroll
+        for (int t = 0; t < R; t++) p[q][t * S] = x[q][t];
+      }
     }
   }
 }
 
-template <class P, bool INV, int I = 0> struct StaticFft {
+template <class P, bool INV, bool TWS = false, int ILP = 1, int I = 0> struct StaticFft {
   static __device__ __forceinline__ void run(float2 *col, float2 const *tw, int lane) {
-    static_stage<P, INV, I>(col, tw, lane);
+    // big radices have no registers for a second butterfly
+    static_stage<P, INV, I, TWS, (P::rad(I) <= 12 ? ILP : 1)>(col, tw, lane);
     __syncwarp();
-    StaticFft<P, INV, I + 1>::run(col, tw, lane);
+    StaticFft<P, INV, TWS, ILP, I + 1>::run(col, tw, lane);
   }
 };
-template <class P, bool INV> struct StaticFft<P, INV, P::nst> {
+template <class P, bool INV, bool TWS, int ILP> struct StaticFft<P, INV, TWS, ILP, P::nst> {
   static __device__ __forceinline__ void run(float2 *, float2 const *, int) {}
+};
+
+// Same, with a group of WPC warps (NL = 32*WPC lanes) sharing one column; stages are separated
+// by the named barrier `bar_id` that only the group's NL threads use.
+template <class P, bool INV, int WPC, int I = 0> struct StaticFftGroup {
+  static __device__ __forceinline__ void run(float2 *col, float2 const *tw, int glane, int bar_id) {
+    static_stage<P, INV, I, true, 1, 32 * WPC>(col, tw, glane);
+    if (WPC == 1)
+      __syncwarp();
+    else
+      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * WPC) : "memory");
+    StaticFftGroup<P, INV, WPC, I + 1>::run(col, tw, glane, bar_id);
+  }
+};
+template <class P, bool INV, int WPC> struct StaticFftGroup<P, INV, WPC, P::nst> {
+  static __device__ __forceinline__ void run(float2 *, float2 const *, int, int) {}
 };
 
 // ---- shared-memory bulk copies (TMA, 1-D): cp.async.bulk + mbarrier -------------------------

@@ -38,7 +38,13 @@ struct Pass1Args {
   long first_new;       // index (in complex elements) of the first NEW element of a window, for stats
   float2 *mid;          // [block][k1][n2]
   IngestStats *stats;   // or nullptr
+  unsigned long long *dbg;  // or nullptr: per-CTA phase timestamps (globaltimer ns) for tools/phase_trace.py
 };
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // exp(-2*pi*i*e/n) from a double-precision sincospi, rounded once
 __device__ __forceinline__ float2 unit_root_f(long e, long n) {
@@ -178,6 +184,7 @@ struct Pass2Args {
   float2 const *rootD;  // REAL only: W_{2*nc}^{n1*k2} = exp(-i*pi*k2/n2), k2 < n2
   float2 *spec;         // [block][spec_stride]
   long spec_stride;
+  unsigned long long *dbg;  // or nullptr: per-CTA phase timestamps
 };
 
 __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_kernel(Pass2Args const a) {

@@ -25,6 +25,21 @@ using namespace kfft;
 static thread_local std::string g_err;
 static std::atomic<unsigned long long> g_launches{0};
 
+static std::atomic<int> g_tuning[8];      // experiment knobs (kgpu_set_tuning), 0 = default
+extern "C" int kgpu_set_tuning(int key, int value) {
+  if (key < 0 || key >= 8) return -1;
+  g_tuning[key].store(value);
+  return 0;
+}
+static void *g_dbg_buf = nullptr, *g_dbg_buf2 = nullptr;  // per-CTA phase timestamps (tools/phase_trace.py)
+extern "C" int kgpu_set_debug_buffer(void *d_buf) {
+  g_dbg_buf = d_buf;
+  return 0;
+}
+extern "C" int kgpu_set_debug_buffer_rows(void *d_buf) {
+  g_dbg_buf2 = d_buf;
+  return 0;
+}
 static std::atomic<int> g_static_on{1};  // tests can force the generic kernels
 extern "C" int kgpu_use_static_kernels(int on) {
   g_static_on.store(on != 0);
@@ -286,7 +301,8 @@ struct kgpu_master {
   int n_item_ctas = 0;
   float2 *d_rootD = nullptr;
   float2 *d_twA = nullptr, *d_twB = nullptr, *d_rootC = nullptr;  // static-kernel tables
-  int nit = 0;
+  float2 *d_twA64 = nullptr, *d_twB64 = nullptr;                  // same for 64 rows per step
+  int nit = 0, nit64 = 0;
   int static_cols = 0, static_rows = 0;  // which specialised kernels apply (0 = generic)
   float2 *d_mid = nullptr;
   int mid_blocks = 0;
@@ -383,14 +399,29 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
       for (int r = 0; r < 32; r++) tB[(size_t)c * 32 + r] = root(c * r, m->nc);
     }
     for (int k1 = 0; k1 <= n1 / 2; k1++) tC[(size_t)k1] = root(k1, 2 * m->nc);
+    m->nit64 = (n1 + 63) / 64;
+    std::vector<float2> tA64((size_t)n2 * m->nit64), tB64((size_t)n2 * 64);
+    for (long c = 0; c < n2; c++) {
+      for (int it = 0; it < m->nit64; it++) tA64[(size_t)c * m->nit64 + it] = root(c * 64 * it, m->nc);
+      for (int r = 0; r < 64; r++) tB64[(size_t)c * 64 + r] = root(c * r, m->nc);
+    }
+    CUDA_OKP(cudaMalloc(&m->d_twA64, sizeof(float2) * tA64.size()));
+    CUDA_OKP(cudaMalloc(&m->d_twB64, sizeof(float2) * tB64.size()));
+    CUDA_OKP(cudaMemcpy(m->d_twA64, tA64.data(), sizeof(float2) * tA64.size(), cudaMemcpyHostToDevice));
+    CUDA_OKP(cudaMemcpy(m->d_twB64, tB64.data(), sizeof(float2) * tB64.size(), cudaMemcpyHostToDevice));
     CUDA_OKP(cudaMalloc(&m->d_twA, sizeof(float2) * tA.size()));
     CUDA_OKP(cudaMalloc(&m->d_twB, sizeof(float2) * tB.size()));
     CUDA_OKP(cudaMalloc(&m->d_rootC, sizeof(float2) * tC.size()));
     CUDA_OKP(cudaMemcpy(m->d_twA, tA.data(), sizeof(float2) * tA.size(), cudaMemcpyHostToDevice));
     CUDA_OKP(cudaMemcpy(m->d_twB, tB.data(), sizeof(float2) * tB.size(), cudaMemcpyHostToDevice));
     CUDA_OKP(cudaMemcpy(m->d_rootC, tC.data(), sizeof(float2) * tC.size(), cudaMemcpyHostToDevice));
-    size_t const s1 = sizeof(float2) * (size_t)kTile * m->pitch1, s2 = sizeof(float2) * (size_t)kTile * m->pitch2;
-    if (set_smem((const void *)fwd_cols_static<0, S1296>, s1) || set_smem((const void *)fwd_cols_static<1, S1296>, s1) ||
+    size_t const s18 = sizeof(float2) * ((size_t)8 * m->pitch1 + static_tw_count<S1296>() + 8 * 64),
+                 s14 = sizeof(float2) * ((size_t)4 * m->pitch1 + static_tw_count<S1296>()),
+                 s2 = sizeof(float2) * ((size_t)kTile * m->pitch2 + static_tw_count<S1250>());
+    (void)s14;
+    if (set_smem((const void *)fwd_cols_static<0, S1296, 8, 1>, s18) || set_smem((const void *)fwd_cols_static<1, S1296, 8, 1>, s18) ||
+        set_smem((const void *)fwd_cols_static<2, S1296, 8, 1>, s18) || set_smem((const void *)fwd_cols_static<0, S1296, 8, 2>, s18) ||
+        set_smem((const void *)fwd_cols_static<1, S1296, 8, 2>, s18) || set_smem((const void *)fwd_cols_static<2, S1296, 8, 2>, s18) ||
         set_smem((const void *)fwd_rows_static<S1250, true>, s2) || set_smem((const void *)fwd_rows_static<S1250, false>, s2)) {
       kgpu_master_destroy(m);
       return nullptr;
@@ -411,6 +442,8 @@ extern "C" void kgpu_master_destroy(kgpu_master *m) {
   cudaFree(m->d_twA);
   cudaFree(m->d_twB);
   cudaFree(m->d_rootC);
+  cudaFree(m->d_twA64);
+  cudaFree(m->d_twB64);
   cudaFree(m->d_mid);
   cudaFree(m->d_notch);
   delete m;
@@ -461,6 +494,7 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
   a1.first_new = (m->in_type == KGPU_REAL) ? (m->M - 1) / 2 : (m->M - 1);
   a1.mid = m->d_mid;
   a1.stats = (fmt == KGPU_FMT_I16) ? (IngestStats *)d_stats : nullptr;
+  a1.dbg = (unsigned long long *)g_dbg_buf;
   if (a1.stats) CUDA_OK(cudaMemsetAsync(d_stats, 0, sizeof(IngestStats) * (size_t)nblocks, st));
   dim3 const g1((unsigned)((m->sp.n2 + kTile - 1) / kTile), (unsigned)nblocks);
   FwdTables tb;
@@ -471,12 +505,23 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
   bool const use_static = g_static_on.load() != 0;
   {
     ProfScope ps(K_FWD_COLS, st);
-    size_t const s1 = sizeof(float2) * (size_t)kTile * m->pitch1;
     if (use_static && m->static_cols == 1296) {
-      if (fmt == KGPU_FMT_I16)
-        fwd_cols_static<1, S1296><<<g1, kFwdThreads, s1, st>>>(a1, tb);
-      else
-        fwd_cols_static<0, S1296><<<g1, kFwdThreads, s1, st>>>(a1, tb);
+      int const wpc = g_tuning[0].load() == 1 ? 1 : 2;
+      int const f = (fmt != KGPU_FMT_I16) ? 0 : ((derandomize || a1.stats) ? 2 : 1);
+      size_t const s1 = sizeof(float2) * ((size_t)8 * m->pitch1 + static_tw_count<S1296>() + 8 * 64);
+      if (wpc == 1) {
+        if (f == 0) fwd_cols_static<0, S1296, 8, 1><<<g1, 256, s1, st>>>(a1, tb);
+        else if (f == 1) fwd_cols_static<1, S1296, 8, 1><<<g1, 256, s1, st>>>(a1, tb);
+        else fwd_cols_static<2, S1296, 8, 1><<<g1, 256, s1, st>>>(a1, tb);
+      } else {
+        FwdTables t2 = tb;
+        t2.twA = m->d_twA64;
+        t2.twB = m->d_twB64;
+        t2.nit = m->nit64;
+        if (f == 0) fwd_cols_static<0, S1296, 8, 2><<<g1, 512, s1, st>>>(a1, t2);
+        else if (f == 1) fwd_cols_static<1, S1296, 8, 2><<<g1, 512, s1, st>>>(a1, t2);
+        else fwd_cols_static<2, S1296, 8, 2><<<g1, 512, s1, st>>>(a1, t2);
+      }
     } else if (fmt == KGPU_FMT_I16)
       fwd_cols_kernel<1><<<g1, kFwdThreads, m->smem1, st>>>(a1);
     else
@@ -495,14 +540,16 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
   a2.rootD = m->d_rootD;
   a2.spec = (float2 *)d_spec;
   a2.spec_stride = m->spec_stride;
+  a2.dbg = g_dbg_buf2 ? (unsigned long long *)g_dbg_buf2 : nullptr;
   dim3 const g2((unsigned)m->n_item_ctas, (unsigned)nblocks);
   {
     ProfScope ps(K_FWD_ROWS, st);
     if (use_static && m->static_rows == 1250) {
+      size_t const s2 = sizeof(float2) * ((size_t)kTile * m->pitch2 + static_tw_count<S1250>());
       if (a2.real_split)
-        fwd_rows_static<S1250, true><<<g2, kFwdThreads, m->smem2, st>>>(a2, tb);
+        fwd_rows_static<S1250, true><<<g2, kFwdThreads, s2, st>>>(a2, tb);
       else
-        fwd_rows_static<S1250, false><<<g2, kFwdThreads, m->smem2, st>>>(a2, tb);
+        fwd_rows_static<S1250, false><<<g2, kFwdThreads, s2, st>>>(a2, tb);
     } else
       fwd_rows_kernel<<<g2, kFwdThreads, m->smem2, st>>>(a2);
   }
@@ -868,7 +915,7 @@ extern "C" long kgpu_bank_out_offset(kgpu_bank const *b, int idx) {
 }
 
 template <class P> static int launch_chan_static(ChanArgs const &a, int n, int nblocks, cudaStream_t st) {
-  size_t const sm = sizeof(float2) * (size_t)(2 * P::len + 4) * kChanWarps;
+  size_t const sm = sizeof(float2) * ((size_t)(2 * P::len + 4) * kChanWarps + static_tw_count<P>());
   static bool attr_done = false;
   if (!attr_done) {
     if (set_smem((const void *)chan_static<P>, sm)) return -1;

@@ -20,72 +20,100 @@ struct FwdTables {
   int nit;
 };
 
+// largest divisor of n that is <= cap (compile-time batch sizes without remainders)
+constexpr int batch_of(int n, int cap) {
+  int b = 1;
+  for (int d = 1; d <= cap; d++)
+    if (n % d == 0) b = d;
+  return b;
+}
+constexpr int static_pitch(int len) {
+  int p = len;
+  while (p % 16 != 2) p++;
+  return p;
+}
+
 // ------------------------------------------------------------------ pass 1: columns -----------
-template <int FMT, class P>
-__global__ void __launch_bounds__(kFwdThreads, 2) fwd_cols_static(Pass1Args const a, FwdTables const tb) {
+// FMT 0: float pairs; 1: int16 pairs, plain; 2: int16 pairs with de-randomise + energy/clip stats.
+// TILE columns per CTA, WPC warps per column.
+template <int FMT, class P, int TILE, int WPC>
+__global__ void __launch_bounds__(TILE * 32 * WPC, 16 / TILE) fwd_cols_static(Pass1Args const a, FwdTables const tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2 *tile = reinterpret_cast<float2 *>(smem_raw);  // [kTile][pitch]
-  constexpr int N1 = P::len, RPI = kFwdThreads / kTile /*32*/, NIT = (N1 + RPI - 1) / RPI;
+  constexpr int N1 = P::len, PITCH = static_pitch(N1), NT = TILE * 32 * WPC;
+  constexpr int RPI = NT / TILE /*32 rows per step*/, FULL = N1 / RPI, REM = N1 % RPI;
+  float2 *tile = reinterpret_cast<float2 *>(smem_raw);  // [TILE][PITCH]
+  float2 *s_tw = tile + TILE * PITCH;                   // stage twiddles, shared by the columns
+  float2 *s_twA = s_tw + static_tw_count<P>();          // [TILE][FULL+1] inter-pass factors A(n2, it)
   TilePlan const &pl = c_plans[a.plan];
   int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int const c = tid % kTile, r = tid / kTile;
-  int const c0 = blockIdx.x * kTile;
+  int const c = tid % TILE, r = tid / TILE;
+  int const c0 = blockIdx.x * TILE;
   int const blk = blockIdx.y;
-  int const ncols = min(kTile, a.n2 - c0);
+  int const ncols = min(TILE, a.n2 - c0);
   bool const col_ok = c < ncols;
-  long const n2g = c0 + c;
-  float2 *mycol = tile + c * a.pitch;
+  int const n2g = c0 + c;
+  float2 *mycol = tile + c * PITCH;
+  unsigned long long *dbg = a.dbg ? a.dbg + 6 * ((long)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  if (dbg && tid == 0) {
+    dbg[0] = gtimer();
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    dbg[5] = smid;
+  }
+  for (int i = tid; i < static_tw_count<P>(); i += NT) s_tw[i] = __ldg(pl.tw + i);
+  for (int i = tid; i < TILE * (FULL + 1); i += NT) {
+    int const cc = i / (FULL + 1), it = i - cc * (FULL + 1);
+    if (c0 + cc < a.n2 && it < tb.nit) s_twA[i] = __ldg(tb.twA + (long)(c0 + cc) * tb.nit + it);
+  }
+  float2 const twB = col_ok ? __ldg(tb.twB + n2g * RPI + r) : make_float2(1.f, 0.f);
 
   unsigned long long energy = 0;
   unsigned int clips = 0;
-  constexpr int U = 8;
   if (col_ok) {
-    if (FMT == 1) {
-      int const *src = reinterpret_cast<int const *>(a.in) + (long)blk * a.hop + n2g;
+    long const step = (long)RPI * a.n2;
+    constexpr int U = batch_of(FULL, 20);  // rows in flight per thread
+    if (FMT == 0) {
+      float2 const *src = reinterpret_cast<float2 const *>(a.in) + (long)blk * a.hop + (long)r * a.n2 + n2g;
+      float2 *d = mycol + r;
 #pragma unroll 1
-      for (int it0 = 0; it0 < NIT; it0 += U) {
-        int w[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          int const n1 = r + RPI * (it0 + u);
-          w[u] = (n1 < N1) ? __ldg(src + (long)n1 * a.n2) : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          int const n1 = r + RPI * (it0 + u);
-          if (n1 < N1) {
-            short lo = (short)(w[u] & 0xffff), hi = (short)((unsigned)w[u] >> 16);
-            if (a.derandomize) {
-              lo ^= (short)((lo & 1) ? 0xfffe : 0);
-              hi ^= (short)((hi & 1) ? 0xfffe : 0);
-            }
-            if (a.stats && (long)n1 * a.n2 + n2g >= a.first_new) {
-              energy += (unsigned long long)((int)lo * lo) + (unsigned long long)((int)hi * hi);
-              clips += (lo > 32766 || lo < -32766) + (hi > 32766 || hi < -32766);
-            }
-            mycol[n1] = make_float2((float)lo * a.scale, (float)hi * a.scale);
-          }
-        }
-      }
-    } else {
-      float2 const *src = reinterpret_cast<float2 const *>(a.in) + (long)blk * a.hop + n2g;
-#pragma unroll 1
-      for (int it0 = 0; it0 < NIT; it0 += U) {
+      for (int it0 = 0; it0 < FULL; it0 += U, d += U * RPI) {
         float2 w[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-          int const n1 = r + RPI * (it0 + u);
-          w[u] = (n1 < N1) ? __ldg(src + (long)n1 * a.n2) : make_float2(0.f, 0.f);
-        }
+        for (int u = 0; u < U; u++, src += step) w[u] = ldg_stream_f2(src);
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-          int const n1 = r + RPI * (it0 + u);
-          if (n1 < N1) mycol[n1] = w[u];
-        }
+        for (int u = 0; u < U; u++) d[u * RPI] = w[u];
       }
+      if (REM && r < REM) *d = ldg_stream_f2(src);
+    } else {
+      int const *src = reinterpret_cast<int const *>(a.in) + (long)blk * a.hop + (long)r * a.n2 + n2g;
+      float2 *d = mycol + r;
+      float const sc = a.scale;
+      auto conv = [&](int w, int n1) -> float2 {
+        short lo = (short)(w & 0xffff), hi = (short)((unsigned)w >> 16);
+        if (FMT == 2) {
+          if (a.derandomize) {  // lsb set -> flip bits 1..15 (rx888.c:707-712)
+            lo ^= (short)((lo & 1) ? 0xfffe : 0);
+            hi ^= (short)((hi & 1) ? 0xfffe : 0);
+          }
+          if (a.stats && (long)n1 * a.n2 + n2g >= a.first_new) {
+            energy += (unsigned long long)((int)lo * lo) + (unsigned long long)((int)hi * hi);
+            clips += (lo > 32766 || lo < -32766) + (hi > 32766 || hi < -32766);
+          }
+        }
+        return make_float2((float)lo * sc, (float)hi * sc);
+      };
+#pragma unroll 1
+      for (int it0 = 0; it0 < FULL; it0 += U, d += U * RPI) {
+        int w[U];
+#pragma unroll
+        for (int u = 0; u < U; u++, src += step) w[u] = ldg_stream_b32(src);
+#pragma unroll
+        for (int u = 0; u < U; u++) d[u * RPI] = conv(w[u], r + RPI * (it0 + u));
+      }
+      if (REM && r < REM) *d = conv(ldg_stream_b32(src), r + RPI * FULL);
     }
   }
-  if (FMT == 1 && a.stats) {
+  if (FMT == 2 && a.stats) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       energy += __shfl_xor_sync(0xffffffffu, energy, o);
@@ -96,44 +124,52 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_cols_static(Pass1Args cons
       atomicAdd(&a.stats[blk].clips, clips);
     }
   }
+  if (dbg && tid == 0) dbg[1] = gtimer();
   __syncthreads();
-  if (warp < ncols) StaticFft<P, false>::run(tile + warp * a.pitch, pl.tw, lane);
-  __syncthreads();
-  if (col_ok) {
-    float2 *dst = a.mid + (long)blk * a.nc + n2g;
-    float2 const twB = __ldg(tb.twB + n2g * RPI + r);
-    float2 const *twA = tb.twA + n2g * tb.nit;
-    constexpr int V = 8;
-#pragma unroll 1
-    for (int it0 = 0; it0 < NIT; it0 += V) {
-      float2 v[V];
-#pragma unroll
-      for (int u = 0; u < V; u++) {
-        int const k1 = r + RPI * (it0 + u);
-        if (k1 < N1) v[u] = cmul(mycol[static_slot<P>(k1)], cmul(twB, __ldg(twA + it0 + u)));
-      }
-#pragma unroll
-      for (int u = 0; u < V; u++) {
-        int const k1 = r + RPI * (it0 + u);
-        if (k1 < N1) dst[(long)k1 * a.n2] = v[u];
-      }
-    }
+  if (dbg && tid == 0) dbg[2] = gtimer();
+  {
+    int const fc = warp / WPC;  // the column this warp transforms
+    if (fc < ncols) StaticFftGroup<P, false, WPC>::run(tile + fc * PITCH, s_tw, (warp % WPC) * 32 + lane, 1 + fc);
   }
+  __syncthreads();
+  if (dbg && tid == 0) dbg[3] = gtimer();
+  if (col_ok) {
+    long const step = (long)RPI * a.n2;
+    float2 *dst = a.mid + (long)blk * a.nc + (long)r * a.n2 + n2g;
+    float2 const *twA = s_twA + c * (FULL + 1);
+    constexpr int V = batch_of(FULL, 10);
+#pragma unroll 1
+    for (int it0 = 0; it0 < FULL; it0 += V) {
+      float2 v[V], w[V];
+#pragma unroll
+      for (int u = 0; u < V; u++) {
+        w[u] = twA[it0 + u];
+        v[u] = mycol[static_slot<P>(r + RPI * (it0 + u))];
+      }
+#pragma unroll
+      for (int u = 0; u < V; u++, dst += step) *dst = cmul(v[u], cmul(twB, w[u]));
+    }
+    if (REM && r < REM) *dst = cmul(mycol[static_slot<P>(r + RPI * FULL)], cmul(twB, twA[FULL]));
+  }
+  if (dbg && tid == 0) dbg[4] = gtimer();
 }
 
 // ------------------------------------------------------------------ pass 2: rows --------------
 template <class P, bool REAL_SPLIT>
 __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_static(Pass2Args const a, FwdTables const tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2 *tile = reinterpret_cast<float2 *>(smem_raw);  // [kTile][pitch]
-  __shared__ __align__(8) uint64_t bars[kTile];
-  constexpr int N2 = P::len;
+  constexpr int N2 = P::len, PITCH = static_pitch(N2);
   static_assert(N2 % 2 == 0, "bulk row copies need 16-byte multiples");
+  float2 *tile = reinterpret_cast<float2 *>(smem_raw);  // [kTile][PITCH]
+  float2 *s_tw = tile + kTile * PITCH;
+  __shared__ __align__(8) uint64_t bars[kTile];
   TilePlan const &pl = c_plans[a.plan];
   int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int const blk = blockIdx.y;
   constexpr int IPC = REAL_SPLIT ? kTile / 2 : kTile;
   RowItem const *items = a.items + (long)blockIdx.x * IPC;
+  unsigned long long *dbg = a.dbg ? a.dbg + 6 * ((long)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  if (dbg && tid == 0) dbg[0] = gtimer();
   {
     RowItem const it = items[REAL_SPLIT ? warp >> 1 : warp];
     int row = -1;
@@ -143,7 +179,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_static(Pass2Args cons
     } else if (it.kind == kRowPlain) {
       row = it.row_a;
     }
-    float2 *colp = tile + warp * a.pitch;
+    float2 *colp = tile + warp * PITCH;
     if (row >= 0) {
       // one TMA bulk copy brings the whole (contiguous) row; completion lands on this warp's mbarrier
       if (lane == 0) {
@@ -153,19 +189,28 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_static(Pass2Args cons
         bulk_g2s(colp, a.mid + (long)blk * a.nc + (long)row * N2, N2 * 8, &bars[warp]);
       }
       __syncwarp();
+    }
+    // while the rows fly in, stage the twiddles (all warps help, also idle ones)
+    for (int i = tid; i < static_tw_count<P>(); i += kFwdThreads) s_tw[i] = __ldg(pl.tw + i);
+    __syncthreads();
+    if (row >= 0) {
       mbar_wait(&bars[warp], 0);
-      StaticFft<P, false>::run(colp, pl.tw, lane);
+      if (dbg && tid == 0) dbg[1] = gtimer();
+      StaticFft<P, false, true>::run(colp, s_tw, lane);
     }
   }
   __syncthreads();
+  if (dbg && tid == 0) dbg[2] = gtimer();
 
   float2 *spec = a.spec + (long)blk * a.spec_stride;
+  int const n1 = a.n1;
   if (!REAL_SPLIT) {
     int const i = tid % kTile, q0 = tid / kTile;
     RowItem const it = items[i];
     if (it.kind == kRowPlain) {
-      float2 const *colp = tile + i * a.pitch;
+      float2 const *colp = tile + i * PITCH;
       constexpr int QS = kFwdThreads / kTile, V = 8;
+      float2 *dst = spec + it.row_a;
 #pragma unroll 1
       for (int k0 = q0; k0 < N2; k0 += V * QS) {
         float2 v[V];
@@ -174,49 +219,76 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_static(Pass2Args cons
           if (k0 + u * QS < N2) v[u] = colp[static_slot<P>(k0 + u * QS)];
 #pragma unroll
         for (int u = 0; u < V; u++)
-          if (k0 + u * QS < N2) spec[(long)it.row_a + (long)a.n1 * (k0 + u * QS)] = v[u];
+          if (k0 + u * QS < N2) dst[(long)n1 * (k0 + u * QS)] = v[u];
       }
     }
     return;
   }
+  // REAL epilogue.  X[k] = E - i*P, X[Nc-k] = conj(E + i*P) with E/O the even/odd parts of the
+  // (Z[k], conj Z[Nc-k]) pair and P = W_N^k * O.  4 adjacent rows per warp quad -> 32-byte segments.
   constexpr int HALF = kTile / 2, QS = kFwdThreads / HALF;
   int const i = tid % HALF, q0 = tid / HALF;
   RowItem const it = items[i];
   if (it.kind == kRowEmpty) return;
-  float2 const *ca = tile + (2 * i) * a.pitch;
-  float2 const *cb = (it.kind == kRowPair) ? tile + (2 * i + 1) * a.pitch : ca;
+  float2 const *ca = tile + (2 * i) * PITCH;
   float2 const rootC = __ldg(tb.rootC + it.row_a);
-  int const kend = (it.kind == kRowPair) ? N2 : (it.kind == kRowSelf0 ? N2 / 2 + 1 : (N2 + 1) / 2);
-  bool const self0 = it.kind == kRowSelf0;
+  int const nc = (int)a.nc;
+  auto emit = [&](int k2, float2 za, float2 zb, float2 rd) {
+    int const k = it.row_a + n1 * k2;
+    float2 const w = cmul(rootC, rd);
+    float2 const E = make_float2(0.5f * (za.x + zb.x), 0.5f * (za.y - zb.y));
+    float2 const O = make_float2(0.5f * (za.x - zb.x), 0.5f * (za.y + zb.y));
+    float2 const Pp = cmul(w, O);
+    spec[k] = make_float2(E.x + Pp.y, E.y - Pp.x);
+    spec[nc - k] = make_float2(E.x - Pp.y, -(E.y + Pp.x));
+  };
   constexpr int V = 4;
+  if (it.kind == kRowPair) {
+    float2 const *cb = tile + (2 * i + 1) * PITCH;
+    constexpr int NFULL = (N2 / QS) / V * V;  // iterations valid for every q0
 #pragma unroll 1
-  for (int k0 = q0; k0 < kend; k0 += V * QS) {
-    float2 za[V], zb[V], rd[V];
+    for (int j0 = 0; j0 < NFULL; j0 += V) {
+      float2 za[V], zb[V], rd[V];
 #pragma unroll
-    for (int u = 0; u < V; u++) {
-      int const k2 = k0 + u * QS;
-      if (k2 < kend) {
-        int const k2m = self0 ? (k2 == 0 ? 0 : N2 - k2) : N2 - 1 - k2;
+      for (int u = 0; u < V; u++) {
+        int const k2 = q0 + (j0 + u) * QS;
         rd[u] = __ldg(a.rootD + k2);
         za[u] = ca[static_slot<P>(k2)];
-        zb[u] = cb[static_slot<P>(k2m)];
+        zb[u] = cb[static_slot<P>(N2 - 1 - k2)];
+      }
+#pragma unroll
+      for (int u = 0; u < V; u++) emit(q0 + (j0 + u) * QS, za[u], zb[u], rd[u]);
+    }
+    for (int k2 = q0 + NFULL * QS; k2 < N2; k2 += QS)
+      emit(k2, ca[static_slot<P>(k2)], cb[static_slot<P>(N2 - 1 - k2)], __ldg(a.rootD + k2));
+  } else if (it.kind == kRowSelf0) {  // row 0 pairs with itself: k2 <-> N2-k2 (k2 = 0 -> bins 0 and Nc)
+    for (int k2 = q0; k2 <= N2 / 2; k2 += QS) {
+      float2 const za = ca[static_slot<P>(k2)], zb = ca[static_slot<P>(k2 == 0 ? 0 : N2 - k2)];
+      if (2 * k2 == N2) {  // bin Nc/2 pairs with itself: one write
+        float2 const w = cmul(rootC, __ldg(a.rootD + k2));
+        float2 const E = make_float2(0.5f * (za.x + zb.x), 0.5f * (za.y - zb.y));
+        float2 const O = make_float2(0.5f * (za.x - zb.x), 0.5f * (za.y + zb.y));
+        float2 const Pp = cmul(w, O);
+        spec[n1 * k2] = make_float2(E.x + Pp.y, E.y - Pp.x);
+      } else {
+        emit(k2, za, zb, __ldg(a.rootD + k2));
       }
     }
-#pragma unroll
-    for (int u = 0; u < V; u++) {
-      int const k2 = k0 + u * QS;
-      if (k2 < kend) {
-        long const k = (long)it.row_a + (long)a.n1 * k2;
-        float2 const w = cmul(rootC, rd[u]);
-        float2 const E = make_float2(0.5f * (za[u].x + zb[u].x), 0.5f * (za[u].y - zb[u].y));
-        float2 const O = make_float2(0.5f * (za[u].x - zb[u].x), 0.5f * (za[u].y + zb[u].y));
+  } else {  // middle row n1/2 pairs with itself: k2 <-> N2-1-k2
+    for (int k2 = q0; k2 < (N2 + 1) / 2; k2 += QS) {
+      float2 const za = ca[static_slot<P>(k2)], zb = ca[static_slot<P>(N2 - 1 - k2)];
+      if (2 * k2 == N2 - 1) {
+        float2 const w = cmul(rootC, __ldg(a.rootD + k2));
+        float2 const E = make_float2(0.5f * (za.x + zb.x), 0.5f * (za.y - zb.y));
+        float2 const O = make_float2(0.5f * (za.x - zb.x), 0.5f * (za.y + zb.y));
         float2 const Pp = cmul(w, O);
-        spec[k] = make_float2(E.x + Pp.y, E.y - Pp.x);
-        long const km = a.nc - k;
-        if (km != k) spec[km] = make_float2(E.x - Pp.y, -(E.y + Pp.x));
+        spec[it.row_a + n1 * k2] = make_float2(E.x + Pp.y, E.y - Pp.x);
+      } else {
+        emit(k2, za, zb, __ldg(a.rootD + k2));
       }
     }
   }
+  if (dbg && tid < HALF) dbg[3] = gtimer();
 }
 
 // ------------------------------------------------------------------ channels ------------------
@@ -230,13 +302,28 @@ __global__ void __launch_bounds__(kChanWarps * 32) chan_static(ChanArgs const a)
   constexpr int XS = NS + 4;  // staged slice: up to NS bins + alignment slack
   int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int const oi = blockIdx.x * kChanWarps + warp;
-  if (oi >= a.norder) return;
-  ChanDesc const d = a.desc[a.order ? a.order[oi] : a.chan_base + oi];
-  if (d.plan < 0) return;
+  float2 *s_tw = reinterpret_cast<float2 *>(smem_raw) + kChanWarps * (NS + XS);
+  bool const active = oi < a.norder;
+  ChanDesc d;
+  d.plan = -1;
+  if (active) d = a.desc[a.order ? a.order[oi] : a.chan_base + oi];
+  {  // stage twiddles of this plan once per CTA (every descriptor of the launch shares the plan)
+    int const plan0 = a.desc[a.order ? a.order[blockIdx.x * kChanWarps] : a.chan_base + blockIdx.x * kChanWarps].plan;
+    if (plan0 >= 0) {
+      float2 const *gtw = c_plans[plan0].tw;
+      for (int i = threadIdx.x; i < static_tw_count<P>(); i += kChanWarps * 32) s_tw[i] = __ldg(gtw + i);
+    }
+    __syncthreads();
+    if (plan0 < 0 && d.plan >= 0) {  // first descriptor of the CTA disabled: this warp stages for itself
+      float2 const *gtw = c_plans[d.plan].tw;
+      for (int i = lane; i < static_tw_count<P>(); i += 32) s_tw[i] = __ldg(gtw + i);
+      __syncwarp();
+    }
+  }
+  if (!active || d.plan < 0) return;
   int const blk = blockIdx.y;
   float2 *col = reinterpret_cast<float2 *>(smem_raw) + warp * (NS + XS);
   float2 *xs = col + NS;
-  TilePlan const &pl = c_plans[d.plan];
   float2 const *X = a.spec + (long)blk * a.spec_stride;
   float2 const *R = a.resp + d.resp_off;
   float2 *dst = a.out + (long)blk * a.out_stride + d.out_off;
@@ -295,7 +382,7 @@ __global__ void __launch_bounds__(kChanWarps * 32) chan_static(ChanArgs const a)
     }
     __syncwarp();
   }
-  StaticFft<P, true>::run(col, pl.tw, lane);
+  StaticFft<P, true, true>::run(col, s_tw, lane);
   int const first = NS - d.olen;
 #pragma unroll 4
   for (int i = lane; i < d.olen; i += 32) dst[i] = col[static_slot<P>(first + i)];
