@@ -196,24 +196,24 @@ def run_ours(args) -> None:
     hpin = torch.from_numpy(np.concatenate([np.zeros(M - 1, np.int16), host])).pin_memory()
     d_stream = hpin.to(dev)
     ngroups = nstream // B
-    spec = cz.alloc_spectra(B)
+    from ka9q_radio_b200.sharding import PipelinedSharder
+
+    spec2 = [cz.alloc_spectra(B) for _ in range(2)]
+    spec = spec2[0]
     out = cz.alloc_outputs(B)
     comp = torch.cuda.current_stream(dev)
-
-    def step_resident(g: int):
-        if rank == 0 or world == 1:
-            cz.forward(d_stream, B, spec, scale=SCALE, first_block=(g % ngroups) * B)
-        if world > 1:
-            dist.broadcast(spec, src=0)
-        cz.channels(spec, B, out)
+    sharder = PipelinedSharder(
+        rank, world,
+        forward=lambda step, slot: cz.forward(d_stream, B, spec2[slot], scale=SCALE, first_block=(step % ngroups) * B),
+        broadcast=lambda slot: dist.broadcast(spec2[slot], src=0, async_op=True),
+        channels=lambda step, slot: cz.channels(spec2[slot], B, out))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for g in range(args.warmup):
-        step_resident(g)
+    sharder.run(range(args.warmup))
     barrier()
     lib.kgpu_profile_enable(1)
     lib.kgpu_profile_reset()
@@ -224,8 +224,7 @@ def run_ours(args) -> None:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(comp)
-    for g in range(args.steps):
-        step_resident(args.warmup + g)
+    sharder.run(range(args.warmup, args.warmup + args.steps))
     e1.record(comp)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -387,8 +386,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--blocks-per-step", type=int, default=4)
-    ap.add_argument("--stream-blocks", type=int, default=32, help="resident input stream length (blocks)")
+    ap.add_argument("--blocks-per-step", type=int, default=8)
+    ap.add_argument("--stream-blocks", type=int, default=64, help="resident input stream length (blocks)")
     ap.add_argument("--ref-blocks", type=int, default=12, help="blocks per step of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -1,0 +1,77 @@
+"""N>1 host logic on CPU: world_size-2 gloo run of the channel-sharding pipeline.
+
+The compute callbacks here are the ORACLE (test infrastructure); what is under test is the
+orchestration in ka9q_radio_b200/sharding.py that bench.py uses with the CUDA kernels + NCCL:
+partitioning, the two-deep forward/broadcast/channels pipeline, buffer-slot reuse."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def test_channel_groups():
+    from ka9q_radio_b200.sharding import channel_groups
+
+    g = channel_groups(8192, 8)
+    assert [len(r) for r in g] == [1024] * 8 and g[3][0] == 3072
+    g = channel_groups(10, 4)
+    assert [list(r) for r in g] == [[0, 1, 2], [3, 4, 5], [6, 7, 8], [9]]
+    assert [len(r) for r in channel_groups(2, 4)] == [1, 1, 0, 0]
+    assert [len(r) for r in channel_groups(0, 2)] == [0, 0]
+
+
+def _worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    from ka9q_radio_b200.sharding import PipelinedSharder, channel_groups
+    from oracle import oracle as O
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    L, M, nsteps = 4800, 1201, 5
+    N = L + M - 1
+    x = O.siggen_real(nsteps * L, 0.1, 0.02, 0.27, 1.0)
+    chans = [dict(olen=48, shift=900 + 200 * i, low=-0.3, high=0.3, beta=9.0) for i in range(7)]
+    mine = channel_groups(len(chans), world)[rank]
+    resp = {i: O.design_response(60, 48, N, True, -0.3, 0.3, 9.0) for i in mine}
+    spec = [torch.zeros(N // 2 + 1, dtype=torch.complex64) for _ in range(2)]
+    out = {}
+
+    def forward(step, slot):
+        spec[slot].copy_(torch.from_numpy(O.forward(O.block_window(x, L, M, step))))
+
+    def broadcast(slot):
+        return dist.broadcast(spec[slot], src=0, async_op=True)
+
+    def channels(step, slot):
+        X = spec[slot].numpy()
+        for i in mine:
+            out[(step, i)] = O.channel_block(O.KO_REAL, X, resp[i], chans[i]["shift"])[-48:].copy()
+
+    PipelinedSharder(rank, world, forward, broadcast, channels).run(range(nsteps))
+    np.save(Path(tmp) / f"rank{rank}.npy", {k: v for k, v in out.items()}, allow_pickle=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_pipeline_matches_single_process(tmp_path, oracle):
+    import torch.multiprocessing as mp
+
+    port = 29600 + (os.getpid() % 300)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    got = {}
+    for r in range(2):
+        got.update(np.load(tmp_path / f"rank{r}.npy", allow_pickle=True).item())
+    L, M, nsteps = 4800, 1201, 5
+    x = oracle.siggen_real(nsteps * L, 0.1, 0.02, 0.27, 1.0)
+    chans = [dict(olen=48, shift=900 + 200 * i, low=-0.3, high=0.3, beta=9.0) for i in range(7)]
+    ref, _ = oracle.run_stream(x, L, M, chans)
+    assert len(got) == nsteps * len(chans)
+    for (step, i), y in got.items():
+        assert np.array_equal(y, ref[step][i])
