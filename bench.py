@@ -383,10 +383,10 @@ def run_e2e(args, torch, cz, hpin, dev, rank, world, dist, B, ngroups) -> dict:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--blocks-per-step", type=int, default=8)
+    ap.add_argument("--blocks-per-step", type=int, default=16)
     ap.add_argument("--stream-blocks", type=int, default=64, help="resident input stream length (blocks)")
     ap.add_argument("--ref-blocks", type=int, default=12, help="blocks per step of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -254,6 +254,8 @@ int get_tile_plan(int len) {
   }
   float2 *d_tw = nullptr;
   uint16_t *d_perm = nullptr;
+  tw.push_back(make_float2(0.f, 0.f));  // padding: bulk (16-byte granular) copies may read one entry past the end
+  tw.push_back(make_float2(0.f, 0.f));
   if (cudaMalloc(&d_tw, sizeof(float2) * std::max<size_t>(tw.size(), 1)) != cudaSuccess) return -1;
   if (cudaMalloc(&d_perm, sizeof(uint16_t) * (size_t)len) != cudaSuccess) return -1;
   if (!tw.empty()) cudaMemcpy(d_tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice);
@@ -389,7 +391,7 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
     if (plan_is<S1250>(p2)) m->static_rows = 1250;
     int const n2 = m->sp.n2;
     m->nit = (n1 + 31) / 32;
-    std::vector<float2> tA((size_t)n2 * m->nit), tB((size_t)n2 * 32), tC((size_t)n1 / 2 + 1);
+    std::vector<float2> tA((size_t)(n2 + 8) * m->nit, make_float2(0.f, 0.f)), tB((size_t)n2 * 32), tC((size_t)n1 / 2 + 1);
     auto root = [](long e, long n) {
       long double const ang = -2.0L * M_PIl * (long double)(e % n) / (long double)n;
       return make_float2((float)cosl(ang), (float)sinl(ang));
@@ -400,7 +402,7 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
     }
     for (int k1 = 0; k1 <= n1 / 2; k1++) tC[(size_t)k1] = root(k1, 2 * m->nc);
     m->nit64 = (n1 + 63) / 64;
-    std::vector<float2> tA64((size_t)n2 * m->nit64), tB64((size_t)n2 * 64);
+    std::vector<float2> tA64((size_t)(n2 + 8) * m->nit64, make_float2(0.f, 0.f)), tB64((size_t)n2 * 64);
     for (long c = 0; c < n2; c++) {
       for (int it = 0; it < m->nit64; it++) tA64[(size_t)c * m->nit64 + it] = root(c * 64 * it, m->nc);
       for (int r = 0; r < 64; r++) tB64[(size_t)c * 64 + r] = root(c * r, m->nc);
@@ -915,7 +917,7 @@ extern "C" long kgpu_bank_out_offset(kgpu_bank const *b, int idx) {
 }
 
 template <class P> static int launch_chan_static(ChanArgs const &a, int n, int nblocks, cudaStream_t st) {
-  size_t const sm = sizeof(float2) * ((size_t)(2 * P::len + 4) * kChanWarps + static_tw_count<P>());
+  size_t const sm = sizeof(float2) * ((size_t)(2 * P::len + 4) * kChanWarps + static_tw_count<P>() + 2);
   static bool attr_done = false;
   if (!attr_done) {
     if (set_smem((const void *)chan_static<P>, sm)) return -1;

@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(TILE * 32 * WPC, 16 / TILE) fwd_cols_static(Pa
   constexpr int RPI = NT / TILE /*32 rows per step*/, FULL = N1 / RPI, REM = N1 % RPI;
   float2 *tile = reinterpret_cast<float2 *>(smem_raw);  // [TILE][PITCH]
   float2 *s_tw = tile + TILE * PITCH;                   // stage twiddles, shared by the columns
-  float2 *s_twA = s_tw + static_tw_count<P>();          // [TILE][FULL+1] inter-pass factors A(n2, it)
+  float2 *s_twA = s_tw + ((static_tw_count<P>() + 1) & ~1);  // [TILE][FULL+1] inter-pass factors A(n2, it)
   TilePlan const &pl = c_plans[a.plan];
   int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int const c = tid % TILE, r = tid / TILE;
@@ -60,10 +60,16 @@ __global__ void __launch_bounds__(TILE * 32 * WPC, 16 / TILE) fwd_cols_static(Pa
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     dbg[5] = smid;
   }
-  for (int i = tid; i < static_tw_count<P>(); i += NT) s_tw[i] = __ldg(pl.tw + i);
-  for (int i = tid; i < TILE * (FULL + 1); i += NT) {
-    int const cc = i / (FULL + 1), it = i - cc * (FULL + 1);
-    if (c0 + cc < a.n2 && it < tb.nit) s_twA[i] = __ldg(tb.twA + (long)(c0 + cc) * tb.nit + it);
+  // stage twiddles and the tile's inter-pass factors arrive by TMA bulk copies (tables are padded)
+  __shared__ __align__(8) uint64_t tbar;
+  constexpr uint32_t TWB = (uint32_t)((static_tw_count<P>() + 1) & ~1) * 8u, TAB = (uint32_t)(TILE * (FULL + 1)) * 8u;
+  static_assert((TILE * (FULL + 1)) % 2 == 0, "inter-pass factor tile must be a 16-byte multiple");
+  if (tid == 0) {
+    mbar_init(&tbar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(&tbar, TWB + TAB);
+    bulk_g2s(s_tw, pl.tw, TWB, &tbar);
+    bulk_g2s(s_twA, tb.twA + (long)c0 * (FULL + 1), TAB, &tbar);
   }
   float2 const twB = col_ok ? __ldg(tb.twB + n2g * RPI + r) : make_float2(1.f, 0.f);
 
@@ -126,6 +132,7 @@ __global__ void __launch_bounds__(TILE * 32 * WPC, 16 / TILE) fwd_cols_static(Pa
   }
   if (dbg && tid == 0) dbg[1] = gtimer();
   __syncthreads();
+  mbar_wait(&tbar, 0);
   if (dbg && tid == 0) dbg[2] = gtimer();
   {
     int const fc = warp / WPC;  // the column this warp transforms
@@ -163,6 +170,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_static(Pass2Args cons
   float2 *tile = reinterpret_cast<float2 *>(smem_raw);  // [kTile][PITCH]
   float2 *s_tw = tile + kTile * PITCH;
   __shared__ __align__(8) uint64_t bars[kTile];
+  __shared__ __align__(8) uint64_t tbar;
   TilePlan const &pl = c_plans[a.plan];
   int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int const blk = blockIdx.y;
@@ -190,9 +198,16 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_static(Pass2Args cons
       }
       __syncwarp();
     }
-    // while the rows fly in, stage the twiddles (all warps help, also idle ones)
-    for (int i = tid; i < static_tw_count<P>(); i += kFwdThreads) s_tw[i] = __ldg(pl.tw + i);
+    // the stage twiddles come the same way, on their own barrier
+    if (tid == 0) {
+      constexpr uint32_t TWB = (uint32_t)((static_tw_count<P>() + 1) & ~1) * 8u;
+      mbar_init(&tbar, 1);
+      mbar_fence_init();
+      mbar_expect_tx(&tbar, TWB);
+      bulk_g2s(s_tw, pl.tw, TWB, &tbar);
+    }
     __syncthreads();
+    mbar_wait(&tbar, 0);
     if (row >= 0) {
       mbar_wait(&bars[warp], 0);
       if (dbg && tid == 0) dbg[1] = gtimer();
@@ -307,19 +322,25 @@ __global__ void __launch_bounds__(kChanWarps * 32) chan_static(ChanArgs const a)
   ChanDesc d;
   d.plan = -1;
   if (active) d = a.desc[a.order ? a.order[oi] : a.chan_base + oi];
-  {  // stage twiddles of this plan once per CTA (every descriptor of the launch shares the plan)
-    int const plan0 = a.desc[a.order ? a.order[blockIdx.x * kChanWarps] : a.chan_base + blockIdx.x * kChanWarps].plan;
-    if (plan0 >= 0) {
-      float2 const *gtw = c_plans[plan0].tw;
-      for (int i = threadIdx.x; i < static_tw_count<P>(); i += kChanWarps * 32) s_tw[i] = __ldg(gtw + i);
+  // stage twiddles of this plan: one TMA bulk copy per CTA (every descriptor of the launch shares the plan)
+  __shared__ __align__(8) uint64_t tbar;
+  __shared__ int plan_sh;
+  if (threadIdx.x == 0) {
+    int p0 = -1;
+    for (int w = 0; w < kChanWarps && p0 < 0; w++) {
+      int const o = blockIdx.x * kChanWarps + w;
+      if (o < a.norder) p0 = a.desc[a.order ? a.order[o] : a.chan_base + o].plan;
     }
-    __syncthreads();
-    if (plan0 < 0 && d.plan >= 0) {  // first descriptor of the CTA disabled: this warp stages for itself
-      float2 const *gtw = c_plans[d.plan].tw;
-      for (int i = lane; i < static_tw_count<P>(); i += 32) s_tw[i] = __ldg(gtw + i);
-      __syncwarp();
+    plan_sh = p0;
+    mbar_init(&tbar, 1);
+    mbar_fence_init();
+    if (p0 >= 0) {
+      constexpr uint32_t TWB = (uint32_t)((static_tw_count<P>() + 1) & ~1) * 8u;
+      mbar_expect_tx(&tbar, TWB);
+      bulk_g2s(s_tw, c_plans[p0].tw, TWB, &tbar);
     }
   }
+  __syncthreads();
   if (!active || d.plan < 0) return;
   int const blk = blockIdx.y;
   float2 *col = reinterpret_cast<float2 *>(smem_raw) + warp * (NS + XS);
@@ -382,6 +403,7 @@ __global__ void __launch_bounds__(kChanWarps * 32) chan_static(ChanArgs const a)
     }
     __syncwarp();
   }
+  mbar_wait(&tbar, 0);
   StaticFft<P, true, true>::run(col, s_tw, lane);
   int const first = NS - d.olen;
 #pragma unroll 4

@@ -311,3 +311,151 @@ def test_run_one_matches_batched(oracle, cuda_dev):
         ref = cz.channel_slice(out, i)[1]
         assert torch.equal(one[: ref.numel()], ref)
     cz.close()
+
+
+# ------------------------------------------------------------------ BASELINE.json configs ------
+def _tone_stream_i16(oracle, nsamp, fs, freqs, amp_db=-30.0, noise_db=-50.0, seed=1):
+    return oracle.siggen_tones_i16(nsamp, [f / fs for f in freqs], [10 ** (amp_db / 20)] * len(freqs), 10 ** (noise_db / 20), seed)
+
+
+def test_cfg2_full_size_channels_subset(oracle, cuda_dev):
+    """cfg-2 at full size: 1024 NBFM channels on the 25 kHz raster + 8 inverted (negative-shift)
+    channels, 2 blocks; every 37th channel and all inverted ones are checked against the oracle."""
+    from ka9q_radio_b200 import capi
+
+    L, M, fs, nb = 2592000, 648001, 129.6e6, 2
+    shifts = [750_000 + 625 * k for k in range(1024)] + [-(750_000 + 625 * k) for k in (0, 3, 64, 100, 511, 700, 900, 1023)]
+    tones = [30.0e6 + 25e3 * k for k in (0, 3, 37, 64, 100, 511, 700, 900, 1023, 407)]
+    xi = _tone_stream_i16(oracle, nb * L, fs, tones)
+    scale = np.float32(10 ** (3 / 20) / 32768)
+    xf, _, _ = oracle.convert_i16(xi, scale)
+    cz = _mk(L, M, capi.KGPU_REAL, cuda_dev, cap=len(shifts))
+    for s in shifts:
+        cz.add_channel(480, s, -8000 / 24000, 8000 / 24000, 11.0)
+    spec, out = cz.alloc_spectra(nb), cz.alloc_outputs(nb)
+    cz.forward(cz.stage_stream(xi), nb, spec, scale=float(scale))
+    cz.channels(spec, nb, out)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    R = oracle.design_response(600, 480, L + M - 1, True, -1 / 3, 1 / 3, 11.0)
+    check = list(range(0, 1024, 37)) + list(range(1024, len(shifts)))
+    loud = 0.0
+    worst = 0.0
+    for b in range(nb):
+        X = oracle.forward(oracle.block_window(xf, L, M, b))
+        refs = {c: oracle.channel_block(oracle.KO_REAL, X, R, shifts[c])[-480:] for c in check}
+        loud = max(loud, max(np.abs(r).max() for r in refs.values()))
+        for c, r in refs.items():
+            g = got[b, c * 480:(c + 1) * 480]
+            # noise-only channels sit ~60 dB below the tones: measure against the louder of (this channel, 1e-3 of the loudest)
+            worst = max(worst, np.abs(g - r).max() / max(np.abs(r).max(), 1e-3 * loud))
+    cz.close()
+    assert worst < TOL, worst
+
+
+def test_cfg3_mixed_rates_full_size(oracle, cuda_dev):
+    """cfg-3: RX888 input, SSB channels at 12/24/48 kHz (preset usb: +50..+3000 Hz, beta 11) in one bank."""
+    from ka9q_radio_b200 import capi
+
+    L, M, fs, nb = 2592000, 648001, 129.6e6, 1
+    N = L + M - 1
+    chans = []
+    for i in range(30):
+        olen = (240, 480, 960)[i % 3]
+        rate = olen * 50
+        f = 1.8e6 + i * 0.94e6
+        _, shift, _ = oracle.compute_tuning(N, fs, f)
+        chans.append(dict(olen=olen, shift=shift, low=50 / rate, high=3000 / rate, beta=11.0, f=f))
+    xi = _tone_stream_i16(oracle, nb * L, fs, [c["f"] + 1000.0 for c in chans[::2]])
+    scale = np.float32(10 ** (3 / 20) / 32768)
+    xf, _, _ = oracle.convert_i16(xi, scale)
+    cz = _mk(L, M, capi.KGPU_REAL, cuda_dev, cap=len(chans))
+    for c in chans:
+        cz.add_channel(c["olen"], c["shift"], c["low"], c["high"], c["beta"])
+    spec, out = cz.alloc_spectra(nb), cz.alloc_outputs(nb)
+    cz.forward(cz.stage_stream(xi), nb, spec, scale=float(scale))
+    cz.channels(spec, nb, out)
+    torch.cuda.synchronize()
+    X = oracle.forward(oracle.block_window(xf, L, M, 0))
+    refs = []
+    for c in chans:
+        pts = c["olen"] * N // L
+        R = oracle.design_response(pts, c["olen"], N, True, c["low"], c["high"], c["beta"])
+        refs.append(oracle.channel_block(oracle.KO_REAL, X, R, c["shift"])[-c["olen"]:])
+    loud = max(np.abs(r).max() for r in refs)
+    for i, r in enumerate(refs):
+        g = cz.channel_slice(out, i).cpu().numpy()[0]
+        assert np.abs(g - r).max() / max(np.abs(r).max(), 1e-3 * loud) < TOL, i
+    cz.close()
+
+
+def test_cfg4_complex_iq_int16(oracle, cuda_dev):
+    """cfg-4: 20 MS/s complex int16 I/Q, N = 500 000 c2c, 512 channels on a 25 kHz raster across
+    -6.4..+6.4 MHz (negative shifts and circular wrap, filter.c:728-793); every 23rd channel checked."""
+    from ka9q_radio_b200 import capi
+
+    L, M, fs, nb = 400000, 100001, 20e6, 2
+    N = L + M - 1
+    rng = np.random.default_rng(11)
+    n = np.arange(nb * L)
+    sig = sum(0.03 * np.exp(2j * np.pi * f / fs * n) for f in (-6.4e6, -1.0e6 + 25e3, 25e3 * 7, 3.2e6, 6.375e6))
+    sig = sig + 0.003 * (rng.standard_normal(nb * L) + 1j * rng.standard_normal(nb * L))
+    iq = np.empty(2 * nb * L, np.int16)
+    iq[0::2] = np.clip(np.round(32767 * sig.real), -32767, 32767)
+    iq[1::2] = np.clip(np.round(32767 * sig.imag), -32767, 32767)
+    scale = np.float32(1.0 / 32768)
+    xf = (iq[0::2].astype(np.float32) * scale + 1j * (iq[1::2].astype(np.float32) * scale)).astype(np.complex64)
+    shifts = [int(round((-6.4e6 + 25e3 * k) / (fs / N))) for k in range(512)]
+    cz = _mk(L, M, capi.KGPU_COMPLEX, cuda_dev, cap=512)
+    for s in shifts:
+        cz.add_channel(480, s, -1 / 3, 1 / 3, 11.0)
+    spec, out = cz.alloc_spectra(nb), cz.alloc_outputs(nb)
+    cz.forward(cz.stage_stream(iq), nb, spec, scale=float(scale))
+    cz.channels(spec, nb, out)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    R = oracle.design_response(600, 480, N, False, -1 / 3, 1 / 3, 11.0)
+    worst, loud = 0.0, 0.0
+    for b in range(nb):
+        X = oracle.forward(oracle.block_window(xf, L, M, b))
+        assert rel_err(spec[b, :N].cpu().numpy(), X) < TOL
+        refs = {c: oracle.channel_block(oracle.KO_COMPLEX, X, R, shifts[c])[-480:] for c in list(range(0, 512, 23)) + [0, 216, 263, 384, 511]}
+        loud = max(loud, max(np.abs(r).max() for r in refs.values()))
+        for c, r in refs.items():
+            g = got[b, c * 480:(c + 1) * 480]
+            worst = max(worst, np.abs(g - r).max() / max(np.abs(r).max(), 1e-3 * loud))
+    cz.close()
+    assert worst < TOL, worst
+
+
+@pytest.mark.parametrize("name", ["real_small", "complex_small", "cfg1_siggen"])
+def test_gpu_matches_golden_fixtures(oracle, cuda_dev, name):
+    """The committed outputs of the reference's own filter.c (tests/golden) reproduced on the GPU."""
+    from pathlib import Path
+
+    from ka9q_radio_b200 import capi
+
+    z = np.load(Path(__file__).resolve().parent / "golden" / f"{name}.npz")
+    L, M, nb, in_type = int(z["L"]), int(z["M"]), int(z["nb"]), int(z["in_type"])
+    a, n, f, s = z["sig"]
+    x = oracle.siggen_real(nb * L, a, n, f, s) if in_type == oracle.KO_REAL else oracle.siggen_complex(nb * L, a, n, f, s)
+    cz = _mk(L, M, in_type, cuda_dev)
+    params = z["chan_params"]
+    for p in params:
+        cz.add_channel(int(p[0]), int(p[1]), float(p[2]), float(p[3]), float(p[4]), isb=bool(p[5]))
+    if not (len(z["notch"]) == 1 and z["notch"][0] == -1):
+        cz.master.set_notches([int(b) for b in z["notch"]])
+    spec, out = cz.alloc_spectra(nb), cz.alloc_outputs(nb)
+    cz.forward(cz.stage_stream(x), nb, spec)
+    cz.apply_notches(spec, nb)
+    cz.channels(spec, nb, out)
+    torch.cuda.synchronize()
+    st = int(z["spec_stride"])
+    sp = spec.cpu().numpy()
+    for b in range(nb):
+        assert rel_err(sp[b, : cz.master.bins][::st], z["spec_sub"][b]) < TOL
+        for i in range(len(params)):
+            ref = z[f"out{i}"][b]
+            g = cz.channel_slice(out, i).cpu().numpy()[b]
+            assert np.abs(g - ref).max() / np.abs(ref).max() < TOL, (b, i)
+    cz.close()
