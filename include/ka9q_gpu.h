@@ -111,8 +111,9 @@ int kgpu_bank_commit(kgpu_bank *b, void *stream);
  * kernel exists (both are parity-tested). Default 1. */
 int kgpu_use_static_kernels(int on);
 
-/* Experiment knobs for A/B measurements (0 = shipped default). key 0/1: butterflies in flight per
- * lane in the cols/rows kernels (1 or 2). */
+/* Experiment knobs for A/B measurements (0 = shipped default). key 0 / 1: warps per column in the
+ * cols / rows kernels (1, default 2); key 2: 2 = plain column pitch in the cols kernel (default:
+ * bank-conflict-free column bases); key 3: 1 = L2 prefetch of the input before the cols kernel. */
 int kgpu_set_tuning(int key, int value);
 
 /* Diagnostics: device buffer (6 uint64 per CTA of the cols kernel) receiving globaltimer stamps

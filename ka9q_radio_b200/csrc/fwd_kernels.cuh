@@ -292,6 +292,14 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_kernel(Pass2Args cons
     emit(k2, ca[__ldg(pl.perm + k2)], cb[__ldg(pl.perm + partner(k2))], __ldg(a.rootD + k2));
 }
 
+// Pull a byte range into L2 with fully coalesced requests (the column pass then reads it in 32-byte
+// pieces at a 5 kB stride, which DRAM serves poorly but L2 serves well).
+__global__ void l2_prefetch_kernel(char const *base, long bytes) {
+  long const lines = (bytes + 127) / 128;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < lines; i += (long)gridDim.x * blockDim.x)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + i * 128));
+}
+
 // ---------------------------------------------------------------------------------------------
 // apply_notch_filters (filter.c:464-474): per listed bin a double-complex EWMA that is
 // subtracted from the bin.  One thread per notch entry, blocks in time order.

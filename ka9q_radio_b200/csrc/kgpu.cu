@@ -194,12 +194,13 @@ std::vector<int> choose_radices(int n) {
   int best_sum = 0;
   if (n < 2) return best;
   search(n, 0, cur, best, best_sum);
-  // even radices first (descending), odd last (descending): large strides first keeps the
-  // power-of-two strides away from the last, unit-stride stages
+  // even radices first (descending): power-of-two strides stay away from the unit-stride stages;
+  // odd ones last, ascending: the biggest odd radix gets stride 1 (no stage twiddles, and its
+  // odd stride is bank-conflict free) -- measured fewer shared-memory wavefronts than descending
   std::stable_sort(best.begin(), best.end(), [](int a, int b) {
     bool const ea = (a % 2 == 0), eb = (b % 2 == 0);
     if (ea != eb) return ea;
-    return a > b;
+    return ea ? a > b : a < b;
   });
   return best;
 }
@@ -417,14 +418,16 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
     CUDA_OKP(cudaMemcpy(m->d_twA, tA.data(), sizeof(float2) * tA.size(), cudaMemcpyHostToDevice));
     CUDA_OKP(cudaMemcpy(m->d_twB, tB.data(), sizeof(float2) * tB.size(), cudaMemcpyHostToDevice));
     CUDA_OKP(cudaMemcpy(m->d_rootC, tC.data(), sizeof(float2) * tC.size(), cudaMemcpyHostToDevice));
-    size_t const s18 = sizeof(float2) * ((size_t)8 * m->pitch1 + static_tw_count<S1296>() + 8 * 64),
+    size_t const s18 = sizeof(float2) * ((size_t)8 * 1328 + static_tw_count<S1296>() + 8 * 64),
                  s14 = sizeof(float2) * ((size_t)4 * m->pitch1 + static_tw_count<S1296>()),
                  s2 = sizeof(float2) * ((size_t)kTile * m->pitch2 + static_tw_count<S1250>());
     (void)s14;
     if (set_smem((const void *)fwd_cols_static<0, S1296, 8, 1>, s18) || set_smem((const void *)fwd_cols_static<1, S1296, 8, 1>, s18) ||
         set_smem((const void *)fwd_cols_static<2, S1296, 8, 1>, s18) || set_smem((const void *)fwd_cols_static<0, S1296, 8, 2>, s18) ||
         set_smem((const void *)fwd_cols_static<1, S1296, 8, 2>, s18) || set_smem((const void *)fwd_cols_static<2, S1296, 8, 2>, s18) ||
-        set_smem((const void *)fwd_rows_static<S1250, true>, s2) || set_smem((const void *)fwd_rows_static<S1250, false>, s2)) {
+        set_smem((const void *)fwd_cols_static<1, S1296, 8, 2, 1>, s18) ||
+        set_smem((const void *)fwd_rows_static<S1250, true, 1>, s2) || set_smem((const void *)fwd_rows_static<S1250, false, 1>, s2) ||
+        set_smem((const void *)fwd_rows_static<S1250, true, 2>, s2) || set_smem((const void *)fwd_rows_static<S1250, false, 2>, s2)) {
       kgpu_master_destroy(m);
       return nullptr;
     }
@@ -499,6 +502,12 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
   a1.dbg = (unsigned long long *)g_dbg_buf;
   if (a1.stats) CUDA_OK(cudaMemsetAsync(d_stats, 0, sizeof(IngestStats) * (size_t)nblocks, st));
   dim3 const g1((unsigned)((m->sp.n2 + kTile - 1) / kTile), (unsigned)nblocks);
+  if (g_tuning[3].load() == 1) {  // experiment: pull the input windows into L2 with coalesced requests first
+    long const esz = (m->in_type == KGPU_REAL) ? (fmt == KGPU_FMT_I16 ? 2 : 4) : (fmt == KGPU_FMT_I16 ? 4 : 8);
+    long const bytes = ((long)(nblocks - 1) * m->L + m->N) * esz;
+    l2_prefetch_kernel<<<148 * 4, 256, 0, st>>>((char const *)d_in, bytes);
+    g_launches++;
+  }
   FwdTables tb;
   tb.twA = m->d_twA;
   tb.twB = m->d_twB;
@@ -510,7 +519,8 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
     if (use_static && m->static_cols == 1296) {
       int const wpc = g_tuning[0].load() == 1 ? 1 : 2;
       int const f = (fmt != KGPU_FMT_I16) ? 0 : ((derandomize || a1.stats) ? 2 : 1);
-      size_t const s1 = sizeof(float2) * ((size_t)8 * m->pitch1 + static_tw_count<S1296>() + 8 * 64);
+      bool const lay1 = (wpc == 2 && f == 1 && g_tuning[2].load() != 2);
+      size_t const s1 = sizeof(float2) * ((size_t)8 * (lay1 ? 1312 : m->pitch1) + static_tw_count<S1296>() + 2 + 8 * 42);
       if (wpc == 1) {
         if (f == 0) fwd_cols_static<0, S1296, 8, 1><<<g1, 256, s1, st>>>(a1, tb);
         else if (f == 1) fwd_cols_static<1, S1296, 8, 1><<<g1, 256, s1, st>>>(a1, tb);
@@ -521,6 +531,7 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
         t2.twB = m->d_twB64;
         t2.nit = m->nit64;
         if (f == 0) fwd_cols_static<0, S1296, 8, 2><<<g1, 512, s1, st>>>(a1, t2);
+        else if (f == 1 && g_tuning[2].load() != 2) fwd_cols_static<1, S1296, 8, 2, 1><<<g1, 512, s1, st>>>(a1, t2);
         else if (f == 1) fwd_cols_static<1, S1296, 8, 2><<<g1, 512, s1, st>>>(a1, t2);
         else fwd_cols_static<2, S1296, 8, 2><<<g1, 512, s1, st>>>(a1, t2);
       }
@@ -548,10 +559,14 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
     ProfScope ps(K_FWD_ROWS, st);
     if (use_static && m->static_rows == 1250) {
       size_t const s2 = sizeof(float2) * ((size_t)kTile * m->pitch2 + static_tw_count<S1250>());
-      if (a2.real_split)
-        fwd_rows_static<S1250, true><<<g2, kFwdThreads, s2, st>>>(a2, tb);
-      else
-        fwd_rows_static<S1250, false><<<g2, kFwdThreads, s2, st>>>(a2, tb);
+      bool const w2 = g_tuning[1].load() != 1;
+      if (a2.real_split) {
+        if (w2) fwd_rows_static<S1250, true, 2><<<g2, 512, s2, st>>>(a2, tb);
+        else fwd_rows_static<S1250, true, 1><<<g2, 256, s2, st>>>(a2, tb);
+      } else {
+        if (w2) fwd_rows_static<S1250, false, 2><<<g2, 512, s2, st>>>(a2, tb);
+        else fwd_rows_static<S1250, false, 1><<<g2, 256, s2, st>>>(a2, tb);
+      }
     } else
       fwd_rows_kernel<<<g2, kFwdThreads, m->smem2, st>>>(a2);
   }

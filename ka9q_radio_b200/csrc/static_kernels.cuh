@@ -35,24 +35,31 @@ constexpr int static_pitch(int len) {
 
 // ------------------------------------------------------------------ pass 1: columns -----------
 // FMT 0: float pairs; 1: int16 pairs, plain; 2: int16 pairs with de-randomise + energy/clip stats.
-// TILE columns per CTA, WPC warps per column.
-template <int FMT, class P, int TILE, int WPC>
+// TILE columns per CTA, WPC warps per column, LAY: shared-memory layout variant (see below).
+template <int FMT, class P, int TILE, int WPC, int LAY = 0>
 __global__ void __launch_bounds__(TILE * 32 * WPC, 16 / TILE) fwd_cols_static(Pass1Args const a, FwdTables const tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int N1 = P::len, PITCH = static_pitch(N1), NT = TILE * 32 * WPC;
-  constexpr int RPI = NT / TILE /*32 rows per step*/, FULL = N1 / RPI, REM = N1 % RPI;
+  // Column c starts at c*PITCH + e(c), PITCH = 0 mod 16 and e = {0,1,2,3,8,9,10,11}: then both the
+  // transposing load (a half-warp holds 8 columns x rows {r, r+4}) and the digit-reversed read of
+  // the store phase (8 columns x slots {s, s+108 = s+12 mod 16}) touch 16 distinct bank pairs.
+  static_assert(TILE == 8, "column base table is written for 8 columns");
+  constexpr int N1 = P::len, PITCH = LAY ? (N1 + 12 + 15) / 16 * 16 : static_pitch(N1), NT = TILE * 32 * WPC;
+  constexpr int RPI = NT / TILE /*rows per step*/, FULL = N1 / RPI, REM = N1 % RPI;
+  auto colbase = [](int cc) { return LAY ? cc * PITCH + (cc < 4 ? cc : cc + 4) : cc * PITCH; };
   float2 *tile = reinterpret_cast<float2 *>(smem_raw);  // [TILE][PITCH]
   float2 *s_tw = tile + TILE * PITCH;                   // stage twiddles, shared by the columns
   float2 *s_twA = s_tw + ((static_tw_count<P>() + 1) & ~1);  // [TILE][FULL+1] inter-pass factors A(n2, it)
   TilePlan const &pl = c_plans[a.plan];
   int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int const c = tid % TILE, r = tid / TILE;
+  int const c = tid % TILE, r = tid / TILE;  // store phase: rows r, r+1 share a half-warp
+  // load phase: rows r, r+4 share a half-warp (warp pairs cover 8 consecutive rows)
+  int const rl = LAY ? 8 * (warp >> 1) + 2 * (warp & 1) + 4 * ((lane >> 3) & 1) + (lane >> 4) : r;
   int const c0 = blockIdx.x * TILE;
   int const blk = blockIdx.y;
   int const ncols = min(TILE, a.n2 - c0);
   bool const col_ok = c < ncols;
   int const n2g = c0 + c;
-  float2 *mycol = tile + c * PITCH;
+  float2 *mycol = tile + colbase(c);
   unsigned long long *dbg = a.dbg ? a.dbg + 6 * ((long)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
   if (dbg && tid == 0) {
     dbg[0] = gtimer();
@@ -79,8 +86,8 @@ __global__ void __launch_bounds__(TILE * 32 * WPC, 16 / TILE) fwd_cols_static(Pa
     long const step = (long)RPI * a.n2;
     constexpr int U = batch_of(FULL, 20);  // rows in flight per thread
     if (FMT == 0) {
-      float2 const *src = reinterpret_cast<float2 const *>(a.in) + (long)blk * a.hop + (long)r * a.n2 + n2g;
-      float2 *d = mycol + r;
+      float2 const *src = reinterpret_cast<float2 const *>(a.in) + (long)blk * a.hop + (long)rl * a.n2 + n2g;
+      float2 *d = mycol + rl;
 #pragma unroll 1
       for (int it0 = 0; it0 < FULL; it0 += U, d += U * RPI) {
         float2 w[U];
@@ -89,10 +96,10 @@ __global__ void __launch_bounds__(TILE * 32 * WPC, 16 / TILE) fwd_cols_static(Pa
 #pragma unroll
         for (int u = 0; u < U; u++) d[u * RPI] = w[u];
       }
-      if (REM && r < REM) *d = ldg_stream_f2(src);
+      if (REM && rl < REM) *d = ldg_stream_f2(src);
     } else {
-      int const *src = reinterpret_cast<int const *>(a.in) + (long)blk * a.hop + (long)r * a.n2 + n2g;
-      float2 *d = mycol + r;
+      int const *src = reinterpret_cast<int const *>(a.in) + (long)blk * a.hop + (long)rl * a.n2 + n2g;
+      float2 *d = mycol + rl;
       float const sc = a.scale;
       auto conv = [&](int w, int n1) -> float2 {
         short lo = (short)(w & 0xffff), hi = (short)((unsigned)w >> 16);
@@ -114,9 +121,9 @@ __global__ void __launch_bounds__(TILE * 32 * WPC, 16 / TILE) fwd_cols_static(Pa
 #pragma unroll
         for (int u = 0; u < U; u++, src += step) w[u] = ldg_stream_b32(src);
 #pragma unroll
-        for (int u = 0; u < U; u++) d[u * RPI] = conv(w[u], r + RPI * (it0 + u));
+        for (int u = 0; u < U; u++) d[u * RPI] = conv(w[u], rl + RPI * (it0 + u));
       }
-      if (REM && r < REM) *d = conv(ldg_stream_b32(src), r + RPI * FULL);
+      if (REM && rl < REM) *d = conv(ldg_stream_b32(src), rl + RPI * FULL);
     }
   }
   if (FMT == 2 && a.stats) {
@@ -136,7 +143,7 @@ __global__ void __launch_bounds__(TILE * 32 * WPC, 16 / TILE) fwd_cols_static(Pa
   if (dbg && tid == 0) dbg[2] = gtimer();
   {
     int const fc = warp / WPC;  // the column this warp transforms
-    if (fc < ncols) StaticFftGroup<P, false, WPC>::run(tile + fc * PITCH, s_tw, (warp % WPC) * 32 + lane, 1 + fc);
+    if (fc < ncols) StaticFftGroup<P, false, WPC>::run(tile + colbase(fc), s_tw, (warp % WPC) * 32 + lane, 1 + fc);
   }
   __syncthreads();
   if (dbg && tid == 0) dbg[3] = gtimer();
@@ -162,10 +169,11 @@ __global__ void __launch_bounds__(TILE * 32 * WPC, 16 / TILE) fwd_cols_static(Pa
 }
 
 // ------------------------------------------------------------------ pass 2: rows --------------
-template <class P, bool REAL_SPLIT>
-__global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_static(Pass2Args const a, FwdTables const tb) {
+// WPC warps per row (column of the tile).
+template <class P, bool REAL_SPLIT, int WPC>
+__global__ void __launch_bounds__(kTile * 32 * WPC, 2) fwd_rows_static(Pass2Args const a, FwdTables const tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int N2 = P::len, PITCH = static_pitch(N2);
+  constexpr int N2 = P::len, PITCH = static_pitch(N2), NT = kTile * 32 * WPC;
   static_assert(N2 % 2 == 0, "bulk row copies need 16-byte multiples");
   float2 *tile = reinterpret_cast<float2 *>(smem_raw);  // [kTile][PITCH]
   float2 *s_tw = tile + kTile * PITCH;
@@ -179,24 +187,22 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_static(Pass2Args cons
   unsigned long long *dbg = a.dbg ? a.dbg + 6 * ((long)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
   if (dbg && tid == 0) dbg[0] = gtimer();
   {
-    RowItem const it = items[REAL_SPLIT ? warp >> 1 : warp];
+    int const colw = warp / WPC, sub = warp % WPC;  // tile column this warp works on
+    RowItem const it = items[REAL_SPLIT ? colw >> 1 : colw];
     int row = -1;
     if (REAL_SPLIT) {
-      if ((warp & 1) == 0 && it.kind != kRowEmpty) row = it.row_a;
-      if ((warp & 1) == 1 && it.kind == kRowPair) row = it.row_b;
+      if ((colw & 1) == 0 && it.kind != kRowEmpty) row = it.row_a;
+      if ((colw & 1) == 1 && it.kind == kRowPair) row = it.row_b;
     } else if (it.kind == kRowPlain) {
       row = it.row_a;
     }
-    float2 *colp = tile + warp * PITCH;
-    if (row >= 0) {
-      // one TMA bulk copy brings the whole (contiguous) row; completion lands on this warp's mbarrier
-      if (lane == 0) {
-        mbar_init(&bars[warp], 1);
-        mbar_fence_init();
-        mbar_expect_tx(&bars[warp], N2 * 8);
-        bulk_g2s(colp, a.mid + (long)blk * a.nc + (long)row * N2, N2 * 8, &bars[warp]);
-      }
-      __syncwarp();
+    float2 *colp = tile + colw * PITCH;
+    if (row >= 0 && sub == 0 && lane == 0) {
+      // one TMA bulk copy brings the whole (contiguous) row; completion lands on this column's mbarrier
+      mbar_init(&bars[colw], 1);
+      mbar_fence_init();
+      mbar_expect_tx(&bars[colw], N2 * 8);
+      bulk_g2s(colp, a.mid + (long)blk * a.nc + (long)row * N2, N2 * 8, &bars[colw]);
     }
     // the stage twiddles come the same way, on their own barrier
     if (tid == 0) {
@@ -209,9 +215,9 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_static(Pass2Args cons
     __syncthreads();
     mbar_wait(&tbar, 0);
     if (row >= 0) {
-      mbar_wait(&bars[warp], 0);
+      mbar_wait(&bars[colw], 0);
       if (dbg && tid == 0) dbg[1] = gtimer();
-      StaticFft<P, false, true>::run(colp, s_tw, lane);
+      StaticFftGroup<P, false, WPC>::run(colp, s_tw, sub * 32 + lane, 1 + colw);
     }
   }
   __syncthreads();
@@ -224,7 +230,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_static(Pass2Args cons
     RowItem const it = items[i];
     if (it.kind == kRowPlain) {
       float2 const *colp = tile + i * PITCH;
-      constexpr int QS = kFwdThreads / kTile, V = 8;
+      constexpr int QS = NT / kTile, V = 8;
       float2 *dst = spec + it.row_a;
 #pragma unroll 1
       for (int k0 = q0; k0 < N2; k0 += V * QS) {
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_static(Pass2Args cons
   }
   // REAL epilogue.  X[k] = E - i*P, X[Nc-k] = conj(E + i*P) with E/O the even/odd parts of the
   // (Z[k], conj Z[Nc-k]) pair and P = W_N^k * O.  4 adjacent rows per warp quad -> 32-byte segments.
-  constexpr int HALF = kTile / 2, QS = kFwdThreads / HALF;
+  constexpr int HALF = kTile / 2, QS = NT / HALF;
   int const i = tid % HALF, q0 = tid / HALF;
   RowItem const it = items[i];
   if (it.kind == kRowEmpty) return;
@@ -419,7 +425,7 @@ template <class P> inline bool plan_is(TilePlan const *p) {
 }
 
 using S1296 = SPlan<1296, 12, 12, 9>;
-using S1250 = SPlan<1250, 10, 25, 5>;
+using S1250 = SPlan<1250, 10, 5, 25>;
 using S600 = SPlan<600, 24, 25>;
 using S300 = SPlan<300, 20, 15>;
 using S1200 = SPlan<1200, 12, 10, 10>;
