@@ -67,6 +67,7 @@ def main():
         stride = max(1, len(specs[0]) // 512)
         data["spec_stride"] = stride
         data["spec_sub"] = np.stack([sp[::stride] for sp in specs])
+        data["spec_absmax"] = np.array([np.abs(sp).max() for sp in specs])
         data["spec_sum"] = np.array([np.sum(sp.astype(np.complex128)) for sp in specs])
         data["spec_energy"] = np.array([np.sum(np.abs(sp.astype(np.complex128)) ** 2) for sp in specs])
         for i in range(len(c["chans"])):

@@ -453,7 +453,7 @@ def test_gpu_matches_golden_fixtures(oracle, cuda_dev, name):
     st = int(z["spec_stride"])
     sp = spec.cpu().numpy()
     for b in range(nb):
-        assert rel_err(sp[b, : cz.master.bins][::st], z["spec_sub"][b]) < TOL
+        assert np.abs(sp[b, : cz.master.bins][::st] - z["spec_sub"][b]).max() / z["spec_absmax"][b] < TOL
         for i in range(len(params)):
             ref = z[f"out{i}"][b]
             g = cz.channel_slice(out, i).cpu().numpy()[b]

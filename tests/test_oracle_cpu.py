@@ -57,7 +57,8 @@ def test_restatement_matches_golden(oracle, name):
     outs, specs = oracle.run_stream(x, int(z["L"]), int(z["M"]), chans, notch_bins=notch, keep_spectra=True)
     st = int(z["spec_stride"])
     for b in range(int(z["nb"])):
-        assert rel_err(specs[b][::st], z["spec_sub"][b]) < 1e-6
+        # error measured against the block's largest bin (the sub-sample may miss the carrier)
+        assert np.abs(specs[b][::st] - z["spec_sub"][b]).max() / z["spec_absmax"][b] < 2e-6
         assert abs(np.sum(np.abs(specs[b].astype(np.complex128)) ** 2) - z["spec_energy"][b]) < 1e-6 * z["spec_energy"][b]
         for i in range(len(chans)):
             ref = z[f"out{i}"][b]
