@@ -13,6 +13,7 @@ namespace kfft {
 
 template <int LEN, int... RS> struct SPlan {
   static constexpr int len = LEN;
+  static constexpr int PB = 0;  // padding block: see Padded<>
   static constexpr int nst = sizeof...(RS);
   static constexpr int rad_arr[sizeof...(RS) > 0 ? sizeof...(RS) : 1] = {RS...};
   static constexpr int rad(int i) { return rad_arr[i]; }
@@ -34,6 +35,15 @@ template <int LEN, int... RS> struct SPlan {
     return p == LEN;
   }
 };
+
+// Same plan with one spare element after every PB_ points of a column (physical index
+// p + p/PB_): turns the even unit-stride of a last stage of radix PB_ into an odd one (no bank
+// conflicts).  Supported when every stage has stride % PB_ == 0 or sub-length <= PB_.
+template <int PB_, class Base> struct Padded : Base {
+  static constexpr int PB = PB_;
+};
+template <class P> constexpr int phys_len() { return P::PB ? P::len + P::len / P::PB : P::len; }
+template <class P> __device__ __forceinline__ int phys_of(int p) { return P::PB ? p + p / P::PB : p; }
 
 // slot holding X[k] after the last stage: digits of k in the mixed radix (r0, r1, ...)
 template <class P, int I = 0> struct SlotOf {
@@ -85,6 +95,8 @@ __device__ __forceinline__ void static_stage(float2 *__restrict__ col, float2 co
   using G = StageGeom<P, I>;
   constexpr int R = G::R, NSUB = G::NSUB, S = G::S, NB = G::NB;
   constexpr int ITERS = (NB + NL - 1) / NL;
+  static_assert(P::PB == 0 || S % P::PB == 0 || NSUB <= P::PB, "padding block does not fit this stage");
+  constexpr int SP = (P::PB && S % P::PB == 0) ? S + S / P::PB : S;  // physical element stride
   float2 const *twi = tw + P::tw_off(I);
 #pragma unroll
   for (int it0 = 0; it0 < ITERS; it0 += ILP) {
@@ -99,10 +111,10 @@ __device__ __forceinline__ void static_stage(float2 *__restrict__ col, float2 co
       int b, j;
       G::split(ok[q] ? u : 0, b, j);
       jj[q] = j;
-      p[q] = col + b * NSUB + j;
+      p[q] = col + phys_of<P>(b * NSUB + j);
       if (ok[q]) {
 #pragma unroll
-        for (int m = 0; m < R; m++) x[q][m] = p[q][m * S];
+        for (int m = 0; m < R; m++) x[q][m] = p[q][m * SP];
       }
     }
 #pragma unroll
@@ -122,7 +134,7 @@ __device__ __forceinline__ void static_stage(float2 *__restrict__ col, float2 co
     for (int q = 0; q < ILP; q++) {
       if (ok[q]) {
 #pragma unroll
-        for (int t = 0; t < R; t++) p[q][t * S] = x[q][t];
+        for (int t = 0; t < R; t++) p[q][t * SP] = x[q][t];
       }
     }
   }

@@ -94,6 +94,7 @@ __device__ __forceinline__ void tile_fft(TilePlan const &pl, float2 *col, int la
       KFFT_CASE(20)
       KFFT_CASE(24)
       KFFT_CASE(25)
+      KFFT_CASE(36)
 #undef KFFT_CASE
       default: break;
     }

@@ -221,6 +221,7 @@ int get_tile_plan(int len) {
   if (len > 1) {
     rad = choose_radices(len);
     if (rad.empty()) return -1;
+    if (len == 1296 && getenv("KGPU_R36")) rad = {36, 36};  // experiment, see S1296b
   }
   TilePlan p;
   memset(&p, 0, sizeof p);
@@ -389,6 +390,7 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
   {
     TilePlan const *p1 = host_tile_plan(m->plan1), *p2 = host_tile_plan(m->plan2);
     if (plan_is<S1296>(p1)) m->static_cols = 1296;
+    if (plan_is<S1296b>(p1)) m->static_cols = 12960;
     if (plan_is<S1250>(p2)) m->static_rows = 1250;
     int const n2 = m->sp.n2;
     m->nit = (n1 + 31) / 32;
@@ -426,6 +428,7 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
         set_smem((const void *)fwd_cols_static<2, S1296, 8, 1>, s18) || set_smem((const void *)fwd_cols_static<0, S1296, 8, 2>, s18) ||
         set_smem((const void *)fwd_cols_static<1, S1296, 8, 2>, s18) || set_smem((const void *)fwd_cols_static<2, S1296, 8, 2>, s18) ||
         set_smem((const void *)fwd_cols_static<1, S1296, 8, 2, 1>, s18) ||
+        set_smem((const void *)fwd_cols_static<1, S1296b, 8, 1, 0, 2>, s18) ||
         set_smem((const void *)fwd_rows_static<S1250, true, 1>, s2) || set_smem((const void *)fwd_rows_static<S1250, false, 1>, s2) ||
         set_smem((const void *)fwd_rows_static<S1250, true, 2>, s2) || set_smem((const void *)fwd_rows_static<S1250, false, 2>, s2)) {
       kgpu_master_destroy(m);
@@ -516,7 +519,10 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
   bool const use_static = g_static_on.load() != 0;
   {
     ProfScope ps(K_FWD_COLS, st);
-    if (use_static && m->static_cols == 1296) {
+    if (use_static && m->static_cols == 12960 && fmt == KGPU_FMT_I16) {
+      size_t const s1 = sizeof(float2) * ((size_t)8 * static_pitch(phys_len<S1296b>()) + static_tw_count<S1296b>() + 2 + 8 * 42);
+      fwd_cols_static<1, S1296b, 8, 1, 0, 2><<<g1, 256, s1, st>>>(a1, tb);
+    } else if (use_static && m->static_cols == 1296) {
       int const wpc = g_tuning[0].load() == 1 ? 1 : 2;
       int const f = (fmt != KGPU_FMT_I16) ? 0 : ((derandomize || a1.stats) ? 2 : 1);
       bool const lay1 = (wpc == 2 && f == 1 && g_tuning[2].load() != 2);

@@ -36,14 +36,14 @@ constexpr int static_pitch(int len) {
 // ------------------------------------------------------------------ pass 1: columns -----------
 // FMT 0: float pairs; 1: int16 pairs, plain; 2: int16 pairs with de-randomise + energy/clip stats.
 // TILE columns per CTA, WPC warps per column, LAY: shared-memory layout variant (see below).
-template <int FMT, class P, int TILE, int WPC, int LAY = 0>
-__global__ void __launch_bounds__(TILE * 32 * WPC, 16 / TILE) fwd_cols_static(Pass1Args const a, FwdTables const tb) {
+template <int FMT, class P, int TILE, int WPC, int LAY = 0, int MINB = 2>
+__global__ void __launch_bounds__(TILE * 32 * WPC, MINB) fwd_cols_static(Pass1Args const a, FwdTables const tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // Column c starts at c*PITCH + e(c), PITCH = 0 mod 16 and e = {0,1,2,3,8,9,10,11}: then both the
   // transposing load (a half-warp holds 8 columns x rows {r, r+4}) and the digit-reversed read of
   // the store phase (8 columns x slots {s, s+108 = s+12 mod 16}) touch 16 distinct bank pairs.
   static_assert(TILE == 8, "column base table is written for 8 columns");
-  constexpr int N1 = P::len, PITCH = LAY ? (N1 + 12 + 15) / 16 * 16 : static_pitch(N1), NT = TILE * 32 * WPC;
+  constexpr int N1 = P::len, PITCH = LAY ? (N1 + 12 + 15) / 16 * 16 : static_pitch(phys_len<P>()), NT = TILE * 32 * WPC;
   constexpr int RPI = NT / TILE /*rows per step*/, FULL = N1 / RPI, REM = N1 % RPI;
   auto colbase = [](int cc) { return LAY ? cc * PITCH + (cc < 4 ? cc : cc + 4) : cc * PITCH; };
   float2 *tile = reinterpret_cast<float2 *>(smem_raw);  // [TILE][PITCH]
@@ -87,19 +87,17 @@ __global__ void __launch_bounds__(TILE * 32 * WPC, 16 / TILE) fwd_cols_static(Pa
     constexpr int U = batch_of(FULL, 20);  // rows in flight per thread
     if (FMT == 0) {
       float2 const *src = reinterpret_cast<float2 const *>(a.in) + (long)blk * a.hop + (long)rl * a.n2 + n2g;
-      float2 *d = mycol + rl;
 #pragma unroll 1
-      for (int it0 = 0; it0 < FULL; it0 += U, d += U * RPI) {
+      for (int it0 = 0; it0 < FULL; it0 += U) {
         float2 w[U];
 #pragma unroll
         for (int u = 0; u < U; u++, src += step) w[u] = ldg_stream_f2(src);
 #pragma unroll
-        for (int u = 0; u < U; u++) d[u * RPI] = w[u];
+        for (int u = 0; u < U; u++) mycol[phys_of<P>(rl + RPI * (it0 + u))] = w[u];
       }
-      if (REM && rl < REM) *d = ldg_stream_f2(src);
+      if (REM && rl < REM) mycol[phys_of<P>(rl + RPI * FULL)] = ldg_stream_f2(src);
     } else {
       int const *src = reinterpret_cast<int const *>(a.in) + (long)blk * a.hop + (long)rl * a.n2 + n2g;
-      float2 *d = mycol + rl;
       float const sc = a.scale;
       auto conv = [&](int w, int n1) -> float2 {
         short lo = (short)(w & 0xffff), hi = (short)((unsigned)w >> 16);
@@ -116,14 +114,14 @@ __global__ void __launch_bounds__(TILE * 32 * WPC, 16 / TILE) fwd_cols_static(Pa
         return make_float2((float)lo * sc, (float)hi * sc);
       };
 #pragma unroll 1
-      for (int it0 = 0; it0 < FULL; it0 += U, d += U * RPI) {
+      for (int it0 = 0; it0 < FULL; it0 += U) {
         int w[U];
 #pragma unroll
         for (int u = 0; u < U; u++, src += step) w[u] = ldg_stream_b32(src);
 #pragma unroll
-        for (int u = 0; u < U; u++) d[u * RPI] = conv(w[u], rl + RPI * (it0 + u));
+        for (int u = 0; u < U; u++) mycol[phys_of<P>(rl + RPI * (it0 + u))] = conv(w[u], rl + RPI * (it0 + u));
       }
-      if (REM && rl < REM) *d = conv(ldg_stream_b32(src), rl + RPI * FULL);
+      if (REM && rl < REM) mycol[phys_of<P>(rl + RPI * FULL)] = conv(ldg_stream_b32(src), rl + RPI * FULL);
     }
   }
   if (FMT == 2 && a.stats) {
@@ -158,12 +156,12 @@ __global__ void __launch_bounds__(TILE * 32 * WPC, 16 / TILE) fwd_cols_static(Pa
 #pragma unroll
       for (int u = 0; u < V; u++) {
         w[u] = twA[it0 + u];
-        v[u] = mycol[static_slot<P>(r + RPI * (it0 + u))];
+        v[u] = mycol[phys_of<P>(static_slot<P>(r + RPI * (it0 + u)))];
       }
 #pragma unroll
       for (int u = 0; u < V; u++, dst += step) *dst = cmul(v[u], cmul(twB, w[u]));
     }
-    if (REM && r < REM) *dst = cmul(mycol[static_slot<P>(r + RPI * FULL)], cmul(twB, twA[FULL]));
+    if (REM && r < REM) *dst = cmul(mycol[phys_of<P>(static_slot<P>(r + RPI * FULL))], cmul(twB, twA[FULL]));
   }
   if (dbg && tid == 0) dbg[4] = gtimer();
 }
@@ -426,6 +424,7 @@ template <class P> inline bool plan_is(TilePlan const *p) {
 
 using S1296 = SPlan<1296, 12, 12, 9>;
 using S1250 = SPlan<1250, 10, 5, 25>;
+using S1296b = Padded<36, SPlan<1296, 36, 36>>;  // two fat stages; 36-blocks padded to 37 (odd stride)
 using S600 = SPlan<600, 24, 25>;
 using S300 = SPlan<300, 20, 15>;
 using S1200 = SPlan<1200, 12, 10, 10>;
