@@ -113,7 +113,8 @@ int kgpu_use_static_kernels(int on);
 
 /* Experiment knobs for A/B measurements (0 = shipped default). key 0 / 1: warps per column in the
  * cols / rows kernels (1, default 2); key 2: 2 = plain column pitch in the cols kernel (default:
- * bank-conflict-free column bases); key 3: 1 = L2 prefetch of the input before the cols kernel. */
+ * bank-conflict-free column bases); key 3: 1 = L2 prefetch of the input before the cols kernel;
+ * key 4: 2 = load every stage twiddle (default: load 4, form the rest as products). */
 int kgpu_set_tuning(int key, int value);
 
 /* Diagnostics: device buffer (6 uint64 per CTA of the cols kernel) receiving globaltimer stamps

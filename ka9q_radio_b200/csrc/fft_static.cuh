@@ -90,7 +90,28 @@ template <class P, int I> struct StageGeom {
 // TWS: the twiddle table pointer is in shared memory (plain loads) instead of global (__ldg).
 // ILP: butterflies of consecutive loop iterations handled together (loads of all first, then the
 // arithmetic, then the stores) so one warp keeps ILP independent chains in flight.
-template <class P, bool INV, int I, bool TWS, int ILP, int NL = 32>
+// Stage 1 of the 1296 = 12*12*9 plan (sub-length 108, stride 9): with the plain u -> (u/9, u%9)
+// split a half-warp straddles two 108-blocks whose bases differ by 12 (mod 16) and collides.
+// Walk the 12 x 9 (block, j) grid in 4 x 4 patches instead: 108*b mod 16 takes {0,12,8,4} over four
+// consecutive b, plus j in a run of four -> 16 distinct bank pairs.  j = 8 (12 butterflies) is
+// left over and costs three wavefronts per access instead of one.
+template <> struct StageGeom<SPlan<1296, 12, 12, 9>, 1> {
+  static constexpr int R = 12, NSUB = 108, S = 9, NB = 108;
+  static __device__ __forceinline__ void split(int u, int &b, int &j) {
+    if (u < 96) {
+      int const p = u >> 4, w = u & 15;
+      b = 4 * (p >> 1) + (w >> 2);
+      j = 4 * (p & 1) + (w & 3);
+    } else {
+      b = u - 96;
+      j = 8;
+    }
+  }
+};
+
+// TWC: load only the stage twiddles W^{j*t} for t = 1,2,4,8 and form the others as products of two
+// of them (depth <= 2): shared-memory loads are the scarce resource in these kernels, FMAs are not.
+template <class P, bool INV, int I, bool TWS, int ILP, int NL = 32, bool TWC = false>
 __device__ __forceinline__ void static_stage(float2 *__restrict__ col, float2 const *__restrict__ tw, int lane) {
   using G = StageGeom<P, I>;
   constexpr int R = G::R, NSUB = G::NSUB, S = G::S, NB = G::NB;
@@ -122,10 +143,23 @@ __device__ __forceinline__ void static_stage(float2 *__restrict__ col, float2 co
       if (ok[q]) {
         Dft<R, INV>::run(x[q]);
         if (S > 1) {
+          if (TWC && R <= 16) {
+            float2 w[R];
 #pragma unroll
-          for (int t = 1; t < R; t++) {
-            float2 const w = TWS ? twi[(t - 1) * S + jj[q]] : __ldg(twi + (t - 1) * S + jj[q]);
-            x[q][t] = INV ? cmulc(x[q][t], w) : cmul(x[q][t], w);
+            for (int t = 1; t < R; t <<= 1) w[t] = TWS ? twi[(t - 1) * S + jj[q]] : __ldg(twi + (t - 1) * S + jj[q]);
+#pragma unroll
+            for (int t = 3; t < R; t++) {
+              int const hb = (t >= 8) ? 8 : (t >= 4) ? 4 : 2;  // highest power of two <= t
+              if (t != hb) w[t] = cmul(w[hb], w[t - hb]);
+            }
+#pragma unroll
+            for (int t = 1; t < R; t++) x[q][t] = INV ? cmulc(x[q][t], w[t]) : cmul(x[q][t], w[t]);
+          } else {
+#pragma unroll
+            for (int t = 1; t < R; t++) {
+              float2 const w = TWS ? twi[(t - 1) * S + jj[q]] : __ldg(twi + (t - 1) * S + jj[q]);
+              x[q][t] = INV ? cmulc(x[q][t], w) : cmul(x[q][t], w);
+            }
           }
         }
       }
@@ -154,17 +188,17 @@ template <class P, bool INV, bool TWS, int ILP> struct StaticFft<P, INV, TWS, IL
 
 // Same, with a group of WPC warps (NL = 32*WPC lanes) sharing one column; stages are separated
 // by the named barrier `bar_id` that only the group's NL threads use.
-template <class P, bool INV, int WPC, int I = 0> struct StaticFftGroup {
+template <class P, bool INV, int WPC, bool TWC = false, int I = 0> struct StaticFftGroup {
   static __device__ __forceinline__ void run(float2 *col, float2 const *tw, int glane, int bar_id) {
-    static_stage<P, INV, I, true, 1, 32 * WPC>(col, tw, glane);
+    static_stage<P, INV, I, true, 1, 32 * WPC, TWC>(col, tw, glane);
     if (WPC == 1)
       __syncwarp();
     else
       asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * WPC) : "memory");
-    StaticFftGroup<P, INV, WPC, I + 1>::run(col, tw, glane, bar_id);
+    StaticFftGroup<P, INV, WPC, TWC, I + 1>::run(col, tw, glane, bar_id);
   }
 };
-template <class P, bool INV, int WPC> struct StaticFftGroup<P, INV, WPC, P::nst> {
+template <class P, bool INV, int WPC, bool TWC> struct StaticFftGroup<P, INV, WPC, TWC, P::nst> {
   static __device__ __forceinline__ void run(float2 *, float2 const *, int, int) {}
 };
 

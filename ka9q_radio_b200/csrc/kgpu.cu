@@ -428,6 +428,8 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
         set_smem((const void *)fwd_cols_static<2, S1296, 8, 1>, s18) || set_smem((const void *)fwd_cols_static<0, S1296, 8, 2>, s18) ||
         set_smem((const void *)fwd_cols_static<1, S1296, 8, 2>, s18) || set_smem((const void *)fwd_cols_static<2, S1296, 8, 2>, s18) ||
         set_smem((const void *)fwd_cols_static<1, S1296, 8, 2, 1>, s18) ||
+        set_smem((const void *)fwd_cols_static<1, S1296, 8, 2, 1, 2, true>, s18) ||
+        set_smem((const void *)fwd_rows_static<S1250, true, 2, true>, s2) ||
         set_smem((const void *)fwd_cols_static<1, S1296b, 8, 1, 0, 2>, s18) ||
         set_smem((const void *)fwd_rows_static<S1250, true, 1>, s2) || set_smem((const void *)fwd_rows_static<S1250, false, 1>, s2) ||
         set_smem((const void *)fwd_rows_static<S1250, true, 2>, s2) || set_smem((const void *)fwd_rows_static<S1250, false, 2>, s2)) {
@@ -537,6 +539,7 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
         t2.twB = m->d_twB64;
         t2.nit = m->nit64;
         if (f == 0) fwd_cols_static<0, S1296, 8, 2><<<g1, 512, s1, st>>>(a1, t2);
+        else if (f == 1 && g_tuning[2].load() != 2 && g_tuning[4].load() != 2) fwd_cols_static<1, S1296, 8, 2, 1, 2, true><<<g1, 512, s1, st>>>(a1, t2);
         else if (f == 1 && g_tuning[2].load() != 2) fwd_cols_static<1, S1296, 8, 2, 1><<<g1, 512, s1, st>>>(a1, t2);
         else if (f == 1) fwd_cols_static<1, S1296, 8, 2><<<g1, 512, s1, st>>>(a1, t2);
         else fwd_cols_static<2, S1296, 8, 2><<<g1, 512, s1, st>>>(a1, t2);
@@ -567,7 +570,8 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
       size_t const s2 = sizeof(float2) * ((size_t)kTile * m->pitch2 + static_tw_count<S1250>());
       bool const w2 = g_tuning[1].load() != 1;
       if (a2.real_split) {
-        if (w2) fwd_rows_static<S1250, true, 2><<<g2, 512, s2, st>>>(a2, tb);
+        if (w2 && g_tuning[4].load() != 2) fwd_rows_static<S1250, true, 2, true><<<g2, 512, s2, st>>>(a2, tb);
+        else if (w2) fwd_rows_static<S1250, true, 2><<<g2, 512, s2, st>>>(a2, tb);
         else fwd_rows_static<S1250, true, 1><<<g2, 256, s2, st>>>(a2, tb);
       } else {
         if (w2) fwd_rows_static<S1250, false, 2><<<g2, 512, s2, st>>>(a2, tb);

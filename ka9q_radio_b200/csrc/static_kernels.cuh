@@ -36,7 +36,7 @@ constexpr int static_pitch(int len) {
 // ------------------------------------------------------------------ pass 1: columns -----------
 // FMT 0: float pairs; 1: int16 pairs, plain; 2: int16 pairs with de-randomise + energy/clip stats.
 // TILE columns per CTA, WPC warps per column, LAY: shared-memory layout variant (see below).
-template <int FMT, class P, int TILE, int WPC, int LAY = 0, int MINB = 2>
+template <int FMT, class P, int TILE, int WPC, int LAY = 0, int MINB = 2, bool TWC = false>
 __global__ void __launch_bounds__(TILE * 32 * WPC, MINB) fwd_cols_static(Pass1Args const a, FwdTables const tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // Column c starts at c*PITCH + e(c), PITCH = 0 mod 16 and e = {0,1,2,3,8,9,10,11}: then both the
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(TILE * 32 * WPC, MINB) fwd_cols_static(Pass1Ar
   if (dbg && tid == 0) dbg[2] = gtimer();
   {
     int const fc = warp / WPC;  // the column this warp transforms
-    if (fc < ncols) StaticFftGroup<P, false, WPC>::run(tile + colbase(fc), s_tw, (warp % WPC) * 32 + lane, 1 + fc);
+    if (fc < ncols) StaticFftGroup<P, false, WPC, TWC>::run(tile + colbase(fc), s_tw, (warp % WPC) * 32 + lane, 1 + fc);
   }
   __syncthreads();
   if (dbg && tid == 0) dbg[3] = gtimer();
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(TILE * 32 * WPC, MINB) fwd_cols_static(Pass1Ar
 
 // ------------------------------------------------------------------ pass 2: rows --------------
 // WPC warps per row (column of the tile).
-template <class P, bool REAL_SPLIT, int WPC>
+template <class P, bool REAL_SPLIT, int WPC, bool TWC = false>
 __global__ void __launch_bounds__(kTile * 32 * WPC, 2) fwd_rows_static(Pass2Args const a, FwdTables const tb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int N2 = P::len, PITCH = static_pitch(N2), NT = kTile * 32 * WPC;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kTile * 32 * WPC, 2) fwd_rows_static(Pass2Args
     if (row >= 0) {
       mbar_wait(&bars[colw], 0);
       if (dbg && tid == 0) dbg[1] = gtimer();
-      StaticFftGroup<P, false, WPC>::run(colp, s_tw, sub * 32 + lane, 1 + colw);
+      StaticFftGroup<P, false, WPC, TWC>::run(colp, s_tw, sub * 32 + lane, 1 + colw);
     }
   }
   __syncthreads();
