@@ -293,7 +293,9 @@ def run_ours(args) -> None:
     if dom:
         a = kernels[dom]["alg_gbs"]
         roof = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
-                "traffic": TRAFFIC_NCU.get(dom), "peak_source": peak_src,
+                "traffic": (TRAFFIC_NCU.get(dom) * B) if isinstance(TRAFFIC_NCU.get(dom), (int, float)) else None,
+                "traffic_note": "ncu dram__bytes_read+write per block (profiles/traffic.json) x blocks per launch",
+                "peak_source": peak_src,
                 "note": "algorithmic bytes attributed per kernel: fwd_cols = window read (N*2 B), fwd_rows = spectrum "
                         "write (bins*8 B), chan = slices+responses+outputs; the inter-pass buffer earns no credit"}
     sum_ms = sum(v["avg_ms"] for k, v in kernels.items() if k in alg_per_kernel)
