@@ -18,6 +18,7 @@
 #include "fwd_kernels.cuh"
 #include "plan.cuh"
 #include "static_kernels.cuh"
+#include "static_kernels_v2.cuh"
 
 using namespace kfft;
 
@@ -195,12 +196,12 @@ std::vector<int> choose_radices(int n) {
   if (n < 2) return best;
   search(n, 0, cur, best, best_sum);
   // even radices first (descending): power-of-two strides stay away from the unit-stride stages;
-  // odd ones last, ascending: the biggest odd radix gets stride 1 (no stage twiddles, and its
-  // odd stride is bank-conflict free) -- measured fewer shared-memory wavefronts than descending
+  // odd ones last, descending: the last (unit-stride) stage gets the smallest radix, which is the
+  // one the v2 kernels fuse with the global store / real split (fewest registers per butterfly)
   std::stable_sort(best.begin(), best.end(), [](int a, int b) {
     bool const ea = (a % 2 == 0), eb = (b % 2 == 0);
     if (ea != eb) return ea;
-    return ea ? a > b : a < b;
+    return a > b;
   });
   return best;
 }
@@ -306,6 +307,7 @@ struct kgpu_master {
   float2 *d_rootD = nullptr;
   float2 *d_twA = nullptr, *d_twB = nullptr, *d_rootC = nullptr;  // static-kernel tables
   float2 *d_twA64 = nullptr, *d_twB64 = nullptr;                  // same for 64 rows per step
+  float2 *d_twU = nullptr, *d_twT = nullptr;                      // v2 cols kernel (1296 columns)
   int nit = 0, nit64 = 0;
   int static_cols = 0, static_rows = 0;  // which specialised kernels apply (0 = generic)
   float2 *d_mid = nullptr;
@@ -410,6 +412,17 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
       for (int it = 0; it < m->nit64; it++) tA64[(size_t)c * m->nit64 + it] = root(c * 64 * it, m->nc);
       for (int r = 0; r < 64; r++) tB64[(size_t)c * 64 + r] = root(c * r, m->nc);
     }
+    if (m->static_cols == 1296) {  // inter-pass factors in the v2 kernel's (u, t2) split
+      std::vector<float2> tU((size_t)(n2 + 8) * 144, make_float2(0.f, 0.f)), tT((size_t)(n2 + 8) * 9 + 16, make_float2(0.f, 0.f));
+      for (long c = 0; c < n2; c++) {
+        for (int u = 0; u < 144; u++) tU[(size_t)c * 144 + u] = root(c * (u / 12 + 12 * (u % 12)), m->nc);
+        for (int t = 0; t < 9; t++) tT[(size_t)c * 9 + t] = root(c * 144 * t, m->nc);
+      }
+      CUDA_OKP(cudaMalloc(&m->d_twU, sizeof(float2) * tU.size()));
+      CUDA_OKP(cudaMalloc(&m->d_twT, sizeof(float2) * tT.size()));
+      CUDA_OKP(cudaMemcpy(m->d_twU, tU.data(), sizeof(float2) * tU.size(), cudaMemcpyHostToDevice));
+      CUDA_OKP(cudaMemcpy(m->d_twT, tT.data(), sizeof(float2) * tT.size(), cudaMemcpyHostToDevice));
+    }
     CUDA_OKP(cudaMalloc(&m->d_twA64, sizeof(float2) * tA64.size()));
     CUDA_OKP(cudaMalloc(&m->d_twB64, sizeof(float2) * tB64.size()));
     CUDA_OKP(cudaMemcpy(m->d_twA64, tA64.data(), sizeof(float2) * tA64.size(), cudaMemcpyHostToDevice));
@@ -424,7 +437,10 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
                  s14 = sizeof(float2) * ((size_t)4 * m->pitch1 + static_tw_count<S1296>()),
                  s2 = sizeof(float2) * ((size_t)kTile * m->pitch2 + static_tw_count<S1250>());
     (void)s14;
-    if (set_smem((const void *)fwd_cols_static<0, S1296, 8, 1>, s18) || set_smem((const void *)fwd_cols_static<1, S1296, 8, 1>, s18) ||
+    size_t const sv1 = sizeof(float2) * (8 * 1298 + 1288 + 80), sv2 = sizeof(float2) * (8 * 1250 + 1246);
+    if (set_smem((const void *)fwd_cols_v2<0>, sv1) || set_smem((const void *)fwd_cols_v2<1>, sv1) ||
+        set_smem((const void *)fwd_cols_v2<2>, sv1) || set_smem((const void *)fwd_rows_v2<true>, sv2) ||
+        set_smem((const void *)fwd_rows_v2<false>, sv2) ||set_smem((const void *)fwd_cols_static<0, S1296, 8, 1>, s18) || set_smem((const void *)fwd_cols_static<1, S1296, 8, 1>, s18) ||
         set_smem((const void *)fwd_cols_static<2, S1296, 8, 1>, s18) || set_smem((const void *)fwd_cols_static<0, S1296, 8, 2>, s18) ||
         set_smem((const void *)fwd_cols_static<1, S1296, 8, 2>, s18) || set_smem((const void *)fwd_cols_static<2, S1296, 8, 2>, s18) ||
         set_smem((const void *)fwd_cols_static<1, S1296, 8, 2, 1>, s18) ||
@@ -454,6 +470,8 @@ extern "C" void kgpu_master_destroy(kgpu_master *m) {
   cudaFree(m->d_rootC);
   cudaFree(m->d_twA64);
   cudaFree(m->d_twB64);
+  cudaFree(m->d_twU);
+  cudaFree(m->d_twT);
   cudaFree(m->d_mid);
   cudaFree(m->d_notch);
   delete m;
@@ -521,7 +539,16 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
   bool const use_static = g_static_on.load() != 0;
   {
     ProfScope ps(K_FWD_COLS, st);
-    if (use_static && m->static_cols == 12960 && fmt == KGPU_FMT_I16) {
+    if (use_static && m->static_cols == 1296 && g_tuning[5].load() != 1) {
+      int const f = (fmt != KGPU_FMT_I16) ? 0 : ((derandomize || a1.stats) ? 2 : 1);
+      size_t const sv1 = sizeof(float2) * (8 * 1298 + 1288 + 80);
+      ColsV2Tables t2;
+      t2.twU = m->d_twU;
+      t2.twT = m->d_twT;
+      if (f == 0) fwd_cols_v2<0><<<g1, 288, sv1, st>>>(a1, t2);
+      else if (f == 1) fwd_cols_v2<1><<<g1, 288, sv1, st>>>(a1, t2);
+      else fwd_cols_v2<2><<<g1, 288, sv1, st>>>(a1, t2);
+    } else if (use_static && m->static_cols == 12960 && fmt == KGPU_FMT_I16) {
       size_t const s1 = sizeof(float2) * ((size_t)8 * static_pitch(phys_len<S1296b>()) + static_tw_count<S1296b>() + 2 + 8 * 42);
       fwd_cols_static<1, S1296b, 8, 1, 0, 2><<<g1, 256, s1, st>>>(a1, tb);
     } else if (use_static && m->static_cols == 1296) {
@@ -566,7 +593,11 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
   dim3 const g2((unsigned)m->n_item_ctas, (unsigned)nblocks);
   {
     ProfScope ps(K_FWD_ROWS, st);
-    if (use_static && m->static_rows == 1250) {
+    if (use_static && m->static_rows == 1250 && g_tuning[5].load() != 1) {
+      size_t const sv2 = sizeof(float2) * (8 * 1250 + 1246);
+      if (a2.real_split) fwd_rows_v2<true><<<g2, 256, sv2, st>>>(a2, tb);
+      else fwd_rows_v2<false><<<g2, 256, sv2, st>>>(a2, tb);
+    } else if (use_static && m->static_rows == 1250) {
       size_t const s2 = sizeof(float2) * ((size_t)kTile * m->pitch2 + static_tw_count<S1250>());
       bool const w2 = g_tuning[1].load() != 1;
       if (a2.real_split) {

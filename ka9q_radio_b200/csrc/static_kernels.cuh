@@ -423,7 +423,7 @@ template <class P> inline bool plan_is(TilePlan const *p) {
 }
 
 using S1296 = SPlan<1296, 12, 12, 9>;
-using S1250 = SPlan<1250, 10, 5, 25>;
+using S1250 = SPlan<1250, 10, 25, 5>;
 using S1296b = Padded<36, SPlan<1296, 36, 36>>;  // two fat stages; 36-blocks padded to 37 (odd stride)
 using S600 = SPlan<600, 24, 25>;
 using S300 = SPlan<300, 20, 15>;

@@ -1,0 +1,384 @@
+// static_kernels_v2.cuh -- forward passes with the first and last butterfly stage fused into the
+// global load / store.
+//
+// ncu showed the v1 kernels bound by the L1/shared-memory LSU data pipe (77 % of peak): an
+// in-shared-memory DIF moves every point through shared memory twice per stage plus once on the
+// way in and once on the way out.  Here the lanes of a warp are interleaved over the tile's 8
+// columns (lane = 8*u' + column), so a warp-wide global access still covers 8 adjacent columns
+// (one 32/64-byte segment per row) -- which lets
+//   * stage 0 read its R0 inputs straight from global memory (int16 -> float in registers),
+//   * the last stage write its outputs (times the inter-pass twiddle / through the real split)
+//     straight to global memory,
+// leaving one store, one load+store and one load per point in shared memory instead of eight
+// accesses.  With 288 threads the 8 x 1296 tile divides evenly (864 and 1152 butterflies per
+// stage): no idle lanes.  Column pitch = 2 mod 16 keeps every access pattern here free of bank
+// conflicts (8 even column offsets x 2 consecutive butterflies per half-warp).
+#pragma once
+#include "static_kernels.cuh"
+
+namespace kfft {
+
+using S1250v2 = SPlan<1250, 10, 25, 5>;
+
+// twiddles W^{j*t}, t = 1..R-1, for one butterfly: 4 table loads + products (see static_stage TWC)
+template <int R, int S> __device__ __forceinline__ void load_stage_twiddles(float2 const *twi, int j, float2 (&w)[R]) {
+#pragma unroll
+  for (int t = 1; t < R; t <<= 1) w[t] = twi[(t - 1) * S + j];
+#pragma unroll
+  for (int t = 3; t < R; t++) {
+    int const hb = (t >= 16) ? 16 : (t >= 8) ? 8 : (t >= 4) ? 4 : 2;
+    if (t != hb) w[t] = cmul(w[hb], w[t - hb]);
+  }
+}
+
+struct ColsV2Tables {
+  float2 const *twU;  // [n2][144]  W_nc^{n2 * kbase(u)}, kbase(u) = u/12 + 12*(u%12)   (u = t0*12 + t1)
+  float2 const *twT;  // [n2][9]    W_nc^{n2 * 144 * t2}
+};
+
+// ------------------------------------------------------------------ pass 1: columns -----------
+// FMT 0: float pairs; 1: int16 pairs; 2: int16 pairs + de-randomise + energy/clip statistics.
+template <int FMT>
+__global__ void __launch_bounds__(288, 2) fwd_cols_v2(Pass1Args const a, ColsV2Tables const tb) {
+  using P = SPlan<1296, 12, 12, 9>;
+  constexpr int N1 = 1296, PITCH = 1298, T = 288, UPI = T / 8 /*butterflies per column per iteration*/;
+  constexpr int R0 = 12, S0 = 108, R1 = 12, NSUB1 = 108, S1 = 9, R2 = 9;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *tile = reinterpret_cast<float2 *>(smem_raw);  // [8][PITCH]
+  float2 *s_tw = tile + 8 * PITCH;                      // stage twiddles (1287 entries, padded to 1288)
+  float2 *s_twT = s_tw + 1288;                          // [8][9] (padded to 80)
+  __shared__ __align__(8) uint64_t tbar;
+  TilePlan const &pl = c_plans[a.plan];
+  int const tid = threadIdx.x;
+  int const c = tid & 7, ul = tid >> 3;  // column of the tile, butterfly lane 0..35
+  int const c0 = blockIdx.x * 8, blk = blockIdx.y;
+  int const ncols = min(8, a.n2 - c0);
+  bool const col_ok = c < ncols;
+  int const n2g = c0 + c;
+  float2 *mycol = tile + c * PITCH;
+  if (tid == 0) {
+    mbar_init(&tbar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(&tbar, 1288 * 8 + 80 * 8);
+    bulk_g2s(s_tw, pl.tw, 1288 * 8, &tbar);
+    bulk_g2s(s_twT, tb.twT + (long)c0 * 9, 80 * 8, &tbar);  // table padded by 8 columns + 8 entries
+  }
+  __syncthreads();  // barrier initialised before anybody waits on it
+  // inter-pass factors B'(n2, u) for this thread's four stage-2 butterflies: issued now, used last
+  float2 twU[4];
+#pragma unroll
+  for (int it = 0; it < 4; it++)
+    twU[it] = col_ok ? __ldg(tb.twU + (long)n2g * 144 + ul + UPI * it) : make_float2(1.f, 0.f);
+
+  // ---- stage 0 fused with the load: x[j + 108 m], m = 0..11, straight from global ------------
+  unsigned long long energy = 0;
+  unsigned int clips = 0;
+  if (col_ok) {
+    float const sc = a.scale;
+    long const rstep = (long)S0 * a.n2;  // 108 rows down
+    if (FMT == 0) {
+      float2 const *src = reinterpret_cast<float2 const *>(a.in) + (long)blk * a.hop + n2g;
+      float2 x[3][R0];
+#pragma unroll
+      for (int it = 0; it < 3; it++) {
+        float2 const *p = src + (long)(ul + UPI * it) * a.n2;
+#pragma unroll
+        for (int m = 0; m < R0; m++) x[it][m] = ldg_stream_f2(p + m * rstep);
+      }
+      mbar_wait(&tbar, 0);
+#pragma unroll
+      for (int it = 0; it < 3; it++) {
+        int const j = ul + UPI * it;
+        Dft<R0, false>::run(x[it]);
+        float2 w[R0];
+        load_stage_twiddles<R0, S0>(s_tw, j, w);
+        float2 *d = mycol + j;
+        d[0] = x[it][0];
+#pragma unroll
+        for (int t = 1; t < R0; t++) d[t * S0] = cmul(x[it][t], w[t]);
+      }
+    } else {
+      int const *src = reinterpret_cast<int const *>(a.in) + (long)blk * a.hop + n2g;
+      int raw[3][R0];
+#pragma unroll
+      for (int it = 0; it < 3; it++) {
+        int const *p = src + (long)(ul + UPI * it) * a.n2;
+#pragma unroll
+        for (int m = 0; m < R0; m++) raw[it][m] = ldg_stream_b32(p + m * rstep);
+      }
+      mbar_wait(&tbar, 0);
+#pragma unroll
+      for (int it = 0; it < 3; it++) {
+        int const j = ul + UPI * it;
+        float2 x[R0];
+#pragma unroll
+        for (int m = 0; m < R0; m++) {
+          short lo = (short)(raw[it][m] & 0xffff), hi = (short)((unsigned)raw[it][m] >> 16);
+          if (FMT == 2) {
+            if (a.derandomize) {  // lsb set -> flip bits 1..15 (rx888.c:707-712)
+              lo ^= (short)((lo & 1) ? 0xfffe : 0);
+              hi ^= (short)((hi & 1) ? 0xfffe : 0);
+            }
+            if (a.stats && (long)(j + S0 * m) * a.n2 + n2g >= a.first_new) {
+              energy += (unsigned long long)((int)lo * lo) + (unsigned long long)((int)hi * hi);
+              clips += (lo > 32766 || lo < -32766) + (hi > 32766 || hi < -32766);
+            }
+          }
+          x[m] = make_float2((float)lo * sc, (float)hi * sc);
+        }
+        Dft<R0, false>::run(x);
+        float2 w[R0];
+        load_stage_twiddles<R0, S0>(s_tw, j, w);
+        float2 *d = mycol + j;
+        d[0] = x[0];
+#pragma unroll
+        for (int t = 1; t < R0; t++) d[t * S0] = cmul(x[t], w[t]);
+      }
+    }
+  } else {
+    mbar_wait(&tbar, 0);
+  }
+  if (FMT == 2 && a.stats) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      energy += __shfl_xor_sync(0xffffffffu, energy, o);
+      clips += __shfl_xor_sync(0xffffffffu, clips, o);
+    }
+    if ((tid & 31) == 0 && (energy | clips)) {
+      atomicAdd(&a.stats[blk].energy, energy);
+      atomicAdd(&a.stats[blk].clips, clips);
+    }
+  }
+  __syncthreads();
+
+  // ---- stage 1 in shared memory: 12 blocks of 108, stride 9 -----------------------------------
+  if (col_ok) {
+    float2 const *tw1 = s_tw + P::tw_off(1);
+#pragma unroll 1
+    for (int it = 0; it < 3; it++) {
+      int const u = ul + UPI * it;
+      int const b = u / S1, j = u - b * S1;
+      float2 *p = mycol + b * NSUB1 + j;
+      float2 x[R1], w[R1];
+#pragma unroll
+      for (int m = 0; m < R1; m++) x[m] = p[m * S1];
+      load_stage_twiddles<R1, S1>(tw1, j, w);
+      Dft<R1, false>::run(x);
+      p[0] = x[0];
+#pragma unroll
+      for (int t = 1; t < R1; t++) p[t * S1] = cmul(x[t], w[t]);
+    }
+  }
+  __syncthreads();
+
+  // ---- stage 2 fused with the store: X[k1] * W_nc^{n2 k1} -> mid[k1][n2] ------------------------
+  if (col_ok) {
+    float2 wT[R2];
+#pragma unroll
+    for (int t = 0; t < R2; t++) wT[t] = s_twT[c * 9 + t];
+    float2 *dst = a.mid + (long)blk * a.nc + n2g;
+#pragma unroll
+    for (int it = 0; it < 4; it++) {
+      int const u = ul + UPI * it;        // = t0*12 + t1
+      int const t0 = u / 12, t1 = u - t0 * 12;
+      int const kbase = t0 + 12 * t1;     // k1 = kbase + 144*t2
+      float2 const *p = mycol + u * R2;
+      float2 x[R2];
+#pragma unroll
+      for (int m = 0; m < R2; m++) x[m] = p[m];
+      Dft<R2, false>::run(x);
+      float2 const wb = twU[it];
+#pragma unroll
+      for (int t = 0; t < R2; t++) dst[(long)(kbase + 144 * t) * a.n2] = cmul(x[t], cmul(wb, wT[t]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ pass 2: rows --------------
+// 1250 = 10 * 25 * 5.  Rows arrive by TMA; stages 0 and 1 run in shared memory with the lanes
+// interleaved over the 8 columns; the radix-5 last stage is fused with the real split: the thread
+// that owns butterfly u of row k1 also takes butterfly 249-u of the mirror row N1-k1, which holds
+// exactly the partners Z[Nc-k] of its five outputs (digit complement: 1249-k2 <-> (9-t0,24-t1,4-t2)).
+template <bool REAL_SPLIT>
+__global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTables const tb) {
+  using P = S1250v2;
+  constexpr int N2 = 1250, PITCH = 1250, T = 256;
+  constexpr int R0 = 10, S0 = 125, R1 = 25, NSUB1 = 125, S1 = 5, R2 = 5;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *tile = reinterpret_cast<float2 *>(smem_raw);  // [8][PITCH]
+  float2 *s_tw = tile + 8 * PITCH;
+  __shared__ __align__(8) uint64_t bars[8];
+  __shared__ __align__(8) uint64_t tbar;
+  TilePlan const &pl = c_plans[a.plan];
+  int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int const blk = blockIdx.y;
+  constexpr int IPC = REAL_SPLIT ? 4 : 8;
+  RowItem const *items = a.items + (long)blockIdx.x * IPC;
+  unsigned long long *dbg = a.dbg ? a.dbg + 6 * ((long)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  if (dbg && tid == 0) dbg[0] = gtimer();
+  // which global row sits in which tile column
+  auto row_of = [&](int col) -> int {
+    RowItem const it = items[REAL_SPLIT ? col >> 1 : col];
+    if (REAL_SPLIT) {
+      if ((col & 1) == 0) return it.kind != kRowEmpty ? it.row_a : -1;
+      return it.kind == kRowPair ? it.row_b : -1;
+    }
+    return it.kind == kRowPlain ? it.row_a : -1;
+  };
+  if (lane == 0) {  // warp w fetches column w: one TMA bulk copy of the whole (contiguous) row
+    int const row = row_of(warp);
+    mbar_init(&bars[warp], 1);
+    if (warp == 0) mbar_init(&tbar, 1);
+    mbar_fence_init();
+    if (row >= 0) {
+      mbar_expect_tx(&bars[warp], N2 * 8);
+      bulk_g2s(tile + warp * PITCH, a.mid + (long)blk * a.nc + (long)row * N2, N2 * 8, &bars[warp]);
+    }
+    if (warp == 0) {
+      constexpr uint32_t TWB = (uint32_t)((static_tw_count<P>() + 1) & ~1) * 8u;
+      mbar_expect_tx(&tbar, TWB);
+      bulk_g2s(s_tw, pl.tw, TWB, &tbar);
+    }
+  }
+  __syncthreads();
+  int const c = tid & 7, ul = tid >> 3;  // column, butterfly lane 0..31
+  bool const col_ok = row_of(c) >= 0;
+  mbar_wait(&tbar, 0);
+  if (col_ok) mbar_wait(&bars[c], 0);
+  if (dbg && tid == 0) dbg[1] = gtimer();
+  float2 *mycol = tile + c * PITCH;
+
+  // ---- stage 0: radix 10, stride 125 (125 butterflies per column) ------------------------------
+  if (col_ok) {
+#pragma unroll 1
+    for (int j = ul; j < S0; j += T / 8) {
+      float2 *p = mycol + j;
+      float2 x[R0], w[R0];
+#pragma unroll
+      for (int m = 0; m < R0; m++) x[m] = p[m * S0];
+      load_stage_twiddles<R0, S0>(s_tw, j, w);
+      Dft<R0, false>::run(x);
+      p[0] = x[0];
+#pragma unroll
+      for (int t = 1; t < R0; t++) p[t * S0] = cmul(x[t], w[t]);
+    }
+  }
+  __syncthreads();
+  // ---- stage 1: radix 25, 10 blocks of 125, stride 5 (50 butterflies per column) ---------------
+  if (col_ok) {
+    float2 const *tw1 = s_tw + P::tw_off(1);
+#pragma unroll 1
+    for (int u = ul; u < N2 / R1; u += T / 8) {
+      int const b = u / S1, j = u - b * S1;
+      float2 *p = mycol + b * NSUB1 + j;
+      float2 x[R1];
+#pragma unroll
+      for (int m = 0; m < R1; m++) x[m] = p[m * S1];
+      Dft<R1, false>::run(x);
+#pragma unroll
+      for (int t = 1; t < R1; t++) x[t] = cmul(x[t], tw1[(t - 1) * S1 + j]);
+#pragma unroll
+      for (int t = 0; t < R1; t++) p[t * S1] = x[t];
+    }
+  }
+  __syncthreads();
+  if (dbg && tid == 0) dbg[2] = gtimer();
+
+  float2 *spec = a.spec + (long)blk * a.spec_stride;
+  int const n1 = a.n1;
+  if (!REAL_SPLIT) {
+    // ---- stage 2 fused with the plain store: X[k1 + n1*k2], k2 = t0 + 10 t1 + 250 t2 ---------
+    if (col_ok) {
+      float2 *dst = spec + row_of(c);
+#pragma unroll 1
+      for (int u = ul; u < N2 / R2; u += T / 8) {
+        int const t0 = u / 25, t1 = u - t0 * 25;
+        int const kb = t0 + 10 * t1;
+        float2 const *p = mycol + u * R2;
+        float2 x[R2];
+#pragma unroll
+        for (int m = 0; m < R2; m++) x[m] = p[m];
+        Dft<R2, false>::run(x);
+#pragma unroll
+        for (int t = 0; t < R2; t++) dst[(long)n1 * (kb + 250 * t)] = x[t];
+      }
+    }
+    return;
+  }
+  // ---- stage 2 fused with the real split -----------------------------------------------------
+  // W_N^{n1*k2} = exp(-i*pi*k2/1250); k2 = kb + 250 t2 -> D[kb] * exp(-i*pi*t2/5)
+  int const i = tid & 3, uq = tid >> 2;  // item (row pair) 0..3, butterfly lane 0..63
+  RowItem const it = items[i];
+  int const nc = (int)a.nc;
+  if (it.kind == kRowPair) {
+    float2 const *ca = tile + (2 * i) * PITCH, *cb = tile + (2 * i + 1) * PITCH;
+    float2 const rootC = __ldg(tb.rootC + it.row_a);
+#pragma unroll 1
+    for (int u = uq; u < N2 / R2; u += T / 4) {
+      int const t0 = u / 25, t1 = u - t0 * 25;
+      int const kb = t0 + 10 * t1;
+      float2 const wkb = cmul(rootC, __ldg(a.rootD + kb));  // W_N^{row_a + n1*kb}
+      float2 za[R2], zb[R2];
+      float2 const *pa = ca + u * R2, *pb = cb + (N2 / R2 - 1 - u) * R2;
+#pragma unroll
+      for (int m = 0; m < R2; m++) {
+        za[m] = pa[m];
+        zb[m] = pb[m];
+      }
+      Dft<R2, false>::run(za);
+      Dft<R2, false>::run(zb);
+#pragma unroll
+      for (int t = 0; t < R2; t++) {
+        float2 const A = za[t], B = zb[R2 - 1 - t];
+        float2 const w = (t == 0) ? wkb : cmul(wkb, wroot<10>(t));  // exp(-i*pi*t/5) = W_10^t
+        float2 const E = make_float2(0.5f * (A.x + B.x), 0.5f * (A.y - B.y));
+        float2 const O = make_float2(0.5f * (A.x - B.x), 0.5f * (A.y + B.y));
+        float2 const Pp = cmul(w, O);
+        int const k = it.row_a + n1 * (kb + 250 * t);
+        spec[k] = make_float2(E.x + Pp.y, E.y - Pp.x);          // X[k]    = E - i P
+        spec[nc - k] = make_float2(E.x - Pp.y, -(E.y + Pp.x));  // X[Nc-k] = conj(E + i P)
+      }
+    }
+  }
+  // rows that pair with themselves (k1 = 0 and k1 = n1/2): last stage in place, then the v1 epilogue
+  bool const has_self = (items[0].kind == kRowSelf0 || items[0].kind == kRowSelfMid) ||
+                        (items[1].kind == kRowSelf0 || items[1].kind == kRowSelfMid) ||
+                        (items[2].kind == kRowSelf0 || items[2].kind == kRowSelfMid) ||
+                        (items[3].kind == kRowSelf0 || items[3].kind == kRowSelfMid);
+  if (!has_self) return;  // CTA-uniform
+  for (int s = 0; s < 4; s++) {
+    RowItem const its = items[s];
+    if (its.kind != kRowSelf0 && its.kind != kRowSelfMid) continue;
+    float2 *col = tile + (2 * s) * PITCH;
+    for (int u = tid; u < N2 / R2; u += T) {
+      float2 x[R2];
+#pragma unroll
+      for (int m = 0; m < R2; m++) x[m] = col[u * R2 + m];
+      Dft<R2, false>::run(x);
+#pragma unroll
+      for (int m = 0; m < R2; m++) col[u * R2 + m] = x[m];
+    }
+  }
+  __syncthreads();
+  for (int s = 0; s < 4; s++) {
+    RowItem const its = items[s];
+    if (its.kind != kRowSelf0 && its.kind != kRowSelfMid) continue;
+    float2 const *col = tile + (2 * s) * PITCH;
+    float2 const rootC = __ldg(tb.rootC + its.row_a);
+    bool const self0 = its.kind == kRowSelf0;
+    int const kend = self0 ? N2 / 2 + 1 : (N2 + 1) / 2;
+    for (int k2 = tid; k2 < kend; k2 += T) {
+      int const k2m = self0 ? (k2 == 0 ? 0 : N2 - k2) : N2 - 1 - k2;
+      float2 const A = col[static_slot<P>(k2)], B = col[static_slot<P>(k2m)];
+      float2 const w = cmul(rootC, __ldg(a.rootD + k2));
+      float2 const E = make_float2(0.5f * (A.x + B.x), 0.5f * (A.y - B.y));
+      float2 const O = make_float2(0.5f * (A.x - B.x), 0.5f * (A.y + B.y));
+      float2 const Pp = cmul(w, O);
+      int const k = its.row_a + n1 * k2;
+      spec[k] = make_float2(E.x + Pp.y, E.y - Pp.x);
+      if (nc - k != k) spec[nc - k] = make_float2(E.x - Pp.y, -(E.y + Pp.x));
+    }
+  }
+}
+
+}  // namespace kfft
