@@ -282,11 +282,15 @@ def run_ours(args) -> None:
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback, B200_PROFILING.md)"
     alg_per_kernel = {"fwd_cols": alg_fwd_in * B, "fwd_rows": alg_fwd_out * B, "chan": alg_chan * B}
+    kernel_impl = {"fwd_cols": "fwd_cols_v2<int16> (static 1296 = 12.12.9, stage 0 fused with the load, stage 2 with the store)",
+                   "fwd_rows": "fwd_rows_v2<real> (static 1250 = 10.25.5, TMA row loads, radix-5 stage fused with the real split)",
+                   "chan": "chan_v2<600 = 24.25> (TMA slice+response, product fused into stage 0, output fused into stage 1)"}
     kernels = {}
     for name, (tot_ms, cnt) in prof.items():
         if cnt:
             avg = tot_ms / cnt
-            kernels[name] = {"launches": cnt, "avg_ms": avg, "alg_bytes_per_launch": alg_per_kernel.get(name, 0.0),
+            kernels[name] = {"impl": kernel_impl.get(name), "launches": cnt, "avg_ms": avg,
+                             "alg_bytes_per_launch": alg_per_kernel.get(name, 0.0),
                              "alg_gbs": alg_per_kernel.get(name, 0.0) / (avg * 1e-3) / 1e9 if avg > 0 else None}
     dom = max(kernels, key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches"]) if kernels else None
     roof = None
@@ -413,10 +417,10 @@ def run_e2e(args, torch, cz, hpin, dev, rank, world, dist, B, ngroups) -> dict:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--blocks-per-step", type=int, default=16)
+    ap.add_argument("--blocks-per-step", type=int, default=32)
     ap.add_argument("--stream-blocks", type=int, default=64, help="resident input stream length (blocks)")
     ap.add_argument("--ref-blocks", type=int, default=12, help="blocks per step of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -972,6 +972,18 @@ extern "C" long kgpu_bank_out_offset(kgpu_bank const *b, int idx) {
   return idx < b->nchan ? b->out_off[(size_t)idx] : -1;
 }
 
+template <class P> static int launch_chan_v2(ChanArgs const &a, int n, int nblocks, cudaStream_t st) {
+  size_t const sm = sizeof(float2) * ((size_t)(2 * P::len + 4) * kChanWarps + static_tw_count<P>() + 2);
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (set_smem((const void *)chan_v2<P>, sm)) return -1;
+    attr_done = true;
+  }
+  dim3 const g((unsigned)((n + kChanWarps - 1) / kChanWarps), (unsigned)nblocks);
+  chan_v2<P><<<g, kChanWarps * 32, sm, st>>>(a);
+  return 0;
+}
+
 template <class P> static int launch_chan_static(ChanArgs const &a, int n, int nblocks, cudaStream_t st) {
   size_t const sm = sizeof(float2) * ((size_t)(2 * P::len + 4) * kChanWarps + static_tw_count<P>() + 2);
   static bool attr_done = false;
@@ -1004,6 +1016,10 @@ static int launch_chan(kgpu_bank *b, const void *d_spec, int nblocks, void *d_ou
   g_launches++;
   TilePlan const *tp = host_tile_plan(plan);
   if (g_static_on.load()) {
+    if (g_tuning[6].load() != 1) {
+      if (plan_is<S600>(tp)) return launch_chan_v2<S600>(a, n, nblocks, st);
+      if (plan_is<S300>(tp)) return launch_chan_v2<S300>(a, n, nblocks, st);
+    }
     if (plan_is<S600>(tp)) return launch_chan_static<S600>(a, n, nblocks, st);
     if (plan_is<S300>(tp)) return launch_chan_static<S300>(a, n, nblocks, st);
     if (plan_is<S1200>(tp)) return launch_chan_static<S1200>(a, n, nblocks, st);
