@@ -216,6 +216,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, void const *src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// L2-only bulk prefetch of a contiguous range (address and size multiples of 16)
+__device__ __forceinline__ void bulk_prefetch_l2(void const *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"

@@ -39,11 +39,19 @@ struct Pass1Args {
   float2 *mid;          // [block][k1][n2]
   IngestStats *stats;   // or nullptr
   unsigned long long *dbg;  // or nullptr: per-CTA phase timestamps (globaltimer ns) for tools/phase_trace.py
+  float out_scale;      // v2 kernels: factor folded into the inter-pass twiddle (int16 scale, x0.5 when the split is pre-halved)
+  int pf_dist;          // blocks of look-ahead for the in-kernel L2 prefetch of the input stream (0 = off)
+  int mid_mod;          // experiment (tuning 7): alias the inter-pass buffer of block b onto b % mid_mod (0 = off)
 };
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
+}
+__device__ __forceinline__ unsigned sm_id() {
+  unsigned s;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(s));
+  return s;
 }
 
 // exp(-2*pi*i*e/n) from a double-precision sincospi, rounded once
@@ -185,6 +193,7 @@ struct Pass2Args {
   float2 *spec;         // [block][spec_stride]
   long spec_stride;
   unsigned long long *dbg;  // or nullptr: per-CTA phase timestamps
+  int mid_mod;          // see Pass1Args
 };
 
 __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_kernel(Pass2Args const a) {

@@ -440,7 +440,11 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
     size_t const sv1 = sizeof(float2) * (8 * 1298 + 1288 + 80), sv2 = sizeof(float2) * (8 * 1250 + 1246);
     if (set_smem((const void *)fwd_cols_v2<0>, sv1) || set_smem((const void *)fwd_cols_v2<1>, sv1) ||
         set_smem((const void *)fwd_cols_v2<2>, sv1) || set_smem((const void *)fwd_rows_v2<true>, sv2) ||
-        set_smem((const void *)fwd_rows_v2<false>, sv2) ||set_smem((const void *)fwd_cols_static<0, S1296, 8, 1>, s18) || set_smem((const void *)fwd_cols_static<1, S1296, 8, 1>, s18) ||
+        set_smem((const void *)fwd_rows_v2<false>, sv2) ||
+        set_smem((const void *)fwd_cols_v2<0, 1250>, sv1) || set_smem((const void *)fwd_cols_v2<1, 1250>, sv1) ||
+        set_smem((const void *)fwd_cols_v2<2, 1250>, sv1) || set_smem((const void *)fwd_cols_v2<1, 1250, 1>, sv1) ||
+        set_smem((const void *)fwd_rows_v2<true, 1296, true>, sv2) || set_smem((const void *)fwd_rows_v2<false, 1296, false>, sv2) ||
+        set_smem((const void *)fwd_cols_static<0, S1296, 8, 1>, s18) || set_smem((const void *)fwd_cols_static<1, S1296, 8, 1>, s18) ||
         set_smem((const void *)fwd_cols_static<2, S1296, 8, 1>, s18) || set_smem((const void *)fwd_cols_static<0, S1296, 8, 2>, s18) ||
         set_smem((const void *)fwd_cols_static<1, S1296, 8, 2>, s18) || set_smem((const void *)fwd_cols_static<2, S1296, 8, 2>, s18) ||
         set_smem((const void *)fwd_cols_static<1, S1296, 8, 2, 1>, s18) ||
@@ -523,6 +527,8 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
   a1.mid = m->d_mid;
   a1.stats = (fmt == KGPU_FMT_I16) ? (IngestStats *)d_stats : nullptr;
   a1.dbg = (unsigned long long *)g_dbg_buf;
+  a1.mid_mod = g_tuning[7].load();
+  a1.pf_dist = g_tuning[3].load() >= 2 ? g_tuning[3].load() - 1 : 0;
   if (a1.stats) CUDA_OK(cudaMemsetAsync(d_stats, 0, sizeof(IngestStats) * (size_t)nblocks, st));
   dim3 const g1((unsigned)((m->sp.n2 + kTile - 1) / kTile), (unsigned)nblocks);
   if (g_tuning[3].load() == 1) {  // experiment: pull the input windows into L2 with coalesced requests first
@@ -537,6 +543,7 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
   tb.rootC = m->d_rootC;
   tb.nit = m->nit;
   bool const use_static = g_static_on.load() != 0;
+  bool halved = false;
   {
     ProfScope ps(K_FWD_COLS, st);
     if (use_static && m->static_cols == 1296 && g_tuning[5].load() != 1) {
@@ -545,9 +552,20 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
       ColsV2Tables t2;
       t2.twU = m->d_twU;
       t2.twT = m->d_twT;
-      if (f == 0) fwd_cols_v2<0><<<g1, 288, sv1, st>>>(a1, t2);
-      else if (f == 1) fwd_cols_v2<1><<<g1, 288, sv1, st>>>(a1, t2);
-      else fwd_cols_v2<2><<<g1, 288, sv1, st>>>(a1, t2);
+      // the int16 scale (and the 1/2 of the real split when the row pass is the v2 kernel too) is
+      // folded into the inter-pass twiddle
+      halved = (m->in_type == KGPU_REAL) && m->static_rows == 1250;
+      a1.out_scale = (fmt == KGPU_FMT_I16 ? scale : 1.0f) * (halved ? 0.5f : 1.0f);
+      if (m->sp.n2 == 1250) {
+        if (f == 0) fwd_cols_v2<0, 1250><<<g1, 288, sv1, st>>>(a1, t2);
+        else if (f == 1 && g_tuning[2].load() == 1) fwd_cols_v2<1, 1250, 1><<<g1, 288, sv1, st>>>(a1, t2);
+        else if (f == 1) fwd_cols_v2<1, 1250><<<g1, 288, sv1, st>>>(a1, t2);
+        else fwd_cols_v2<2, 1250><<<g1, 288, sv1, st>>>(a1, t2);
+      } else {
+        if (f == 0) fwd_cols_v2<0><<<g1, 288, sv1, st>>>(a1, t2);
+        else if (f == 1) fwd_cols_v2<1><<<g1, 288, sv1, st>>>(a1, t2);
+        else fwd_cols_v2<2><<<g1, 288, sv1, st>>>(a1, t2);
+      }
     } else if (use_static && m->static_cols == 12960 && fmt == KGPU_FMT_I16) {
       size_t const s1 = sizeof(float2) * ((size_t)8 * static_pitch(phys_len<S1296b>()) + static_tw_count<S1296b>() + 2 + 8 * 42);
       fwd_cols_static<1, S1296b, 8, 1, 0, 2><<<g1, 256, s1, st>>>(a1, tb);
@@ -590,12 +608,15 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
   a2.spec = (float2 *)d_spec;
   a2.spec_stride = m->spec_stride;
   a2.dbg = g_dbg_buf2 ? (unsigned long long *)g_dbg_buf2 : nullptr;
+  a2.mid_mod = g_tuning[7].load();
   dim3 const g2((unsigned)m->n_item_ctas, (unsigned)nblocks);
   {
     ProfScope ps(K_FWD_ROWS, st);
     if (use_static && m->static_rows == 1250 && g_tuning[5].load() != 1) {
       size_t const sv2 = sizeof(float2) * (8 * 1250 + 1246);
-      if (a2.real_split) fwd_rows_v2<true><<<g2, 256, sv2, st>>>(a2, tb);
+      if (a2.real_split && halved) fwd_rows_v2<true, 1296, true><<<g2, 256, sv2, st>>>(a2, tb);
+      else if (a2.real_split) fwd_rows_v2<true><<<g2, 256, sv2, st>>>(a2, tb);
+      else if (m->sp.n1 == 1296) fwd_rows_v2<false, 1296, false><<<g2, 256, sv2, st>>>(a2, tb);
       else fwd_rows_v2<false><<<g2, 256, sv2, st>>>(a2, tb);
     } else if (use_static && m->static_rows == 1250) {
       size_t const s2 = sizeof(float2) * ((size_t)kTile * m->pitch2 + static_tw_count<S1250>());

@@ -38,7 +38,10 @@ struct ColsV2Tables {
 
 // ------------------------------------------------------------------ pass 1: columns -----------
 // FMT 0: float pairs; 1: int16 pairs; 2: int16 pairs + de-randomise + energy/clip statistics.
-template <int FMT>
+// N2C: number of columns as a compile-time constant (0 = read it from the arguments): with it every
+// global address of a thread is one base register plus an immediate.  TWL: stage-0 twiddles by 11
+// table loads instead of 4 loads + 7 products.
+template <int FMT, int N2C = 0, int TWL = 0>
 __global__ void __launch_bounds__(288, 2) fwd_cols_v2(Pass1Args const a, ColsV2Tables const tb) {
   using P = SPlan<1296, 12, 12, 9>;
   constexpr int N1 = 1296, PITCH = 1298, T = 288, UPI = T / 8 /*butterflies per column per iteration*/;
@@ -52,7 +55,15 @@ __global__ void __launch_bounds__(288, 2) fwd_cols_v2(Pass1Args const a, ColsV2T
   int const tid = threadIdx.x;
   int const c = tid & 7, ul = tid >> 3;  // column of the tile, butterfly lane 0..35
   int const c0 = blockIdx.x * 8, blk = blockIdx.y;
-  int const ncols = min(8, a.n2 - c0);
+  int const n2 = N2C ? N2C : a.n2;
+  long const nc = N2C ? (long)N1 * N2C : a.nc;
+  int const mblk = a.mid_mod ? blk % a.mid_mod : blk;
+  unsigned long long *dbg = a.dbg ? a.dbg + 6 * ((long)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  if (dbg && tid == 0) {
+    dbg[0] = gtimer();
+    dbg[5] = sm_id();
+  }
+  int const ncols = min(8, n2 - c0);
   bool const col_ok = c < ncols;
   int const n2g = c0 + c;
   float2 *mycol = tile + c * PITCH;
@@ -63,27 +74,39 @@ __global__ void __launch_bounds__(288, 2) fwd_cols_v2(Pass1Args const a, ColsV2T
     bulk_g2s(s_tw, pl.tw, 1288 * 8, &tbar);
     bulk_g2s(s_twT, tb.twT + (long)c0 * 9, 80 * 8, &tbar);  // table padded by 8 columns + 8 entries
   }
+  // The column gather reads 32-byte pieces at a 5 kB stride, which DRAM serves slowly.  Each CTA
+  // therefore pulls a CONTIGUOUS 1/gridDim.x share of the new samples of block blk + pf_dist into
+  // L2 (bulk prefetch, no registers, no shared memory): by the time that block's CTAs run, their
+  // gather hits L2.
+  if (a.pf_dist > 0 && blk + a.pf_dist < (int)gridDim.y && tid >= 32 && tid < 64) {
+    long const esz = FMT == 0 ? 8 : 4;
+    long const newb = a.hop * esz;                                  // new bytes per block
+    long const share = ((newb / (long)gridDim.x + 15) & ~15L);
+    long const lo = (long)blockIdx.x * share, hi = min(newb, lo + share);
+    char const *base = reinterpret_cast<char const *>(a.in) + ((long)(blk + a.pf_dist) * a.hop + (a.nc - a.hop)) * esz;
+    base = reinterpret_cast<char const *>(reinterpret_cast<unsigned long long>(base) & ~15ULL);
+    for (long o = lo + (long)(tid - 32) * 2048; o < hi; o += 32 * 2048)
+      bulk_prefetch_l2(base + o, (uint32_t)min(2048L, (hi - o) & ~15L));
+  }
   __syncthreads();  // barrier initialised before anybody waits on it
   // inter-pass factors B'(n2, u) for this thread's four stage-2 butterflies: issued now, used last
   float2 twU[4];
 #pragma unroll
   for (int it = 0; it < 4; it++)
-    twU[it] = col_ok ? __ldg(tb.twU + (long)n2g * 144 + ul + UPI * it) : make_float2(1.f, 0.f);
+    twU[it] = col_ok ? ldg_stream_f2(tb.twU + (long)n2g * 144 + ul + UPI * it) : make_float2(1.f, 0.f);
 
   // ---- stage 0 fused with the load: x[j + 108 m], m = 0..11, straight from global ------------
   unsigned long long energy = 0;
   unsigned int clips = 0;
   if (col_ok) {
-    float const sc = a.scale;
-    long const rstep = (long)S0 * a.n2;  // 108 rows down
+    // row of butterfly j = ul + 36 it, input m: j + 108 m  ->  element (ul + 36 it + 108 m) * n2
     if (FMT == 0) {
-      float2 const *src = reinterpret_cast<float2 const *>(a.in) + (long)blk * a.hop + n2g;
+      float2 const *src = reinterpret_cast<float2 const *>(a.in) + (long)blk * a.hop + n2g + (long)ul * n2;
       float2 x[3][R0];
 #pragma unroll
       for (int it = 0; it < 3; it++) {
-        float2 const *p = src + (long)(ul + UPI * it) * a.n2;
 #pragma unroll
-        for (int m = 0; m < R0; m++) x[it][m] = ldg_stream_f2(p + m * rstep);
+        for (int m = 0; m < R0; m++) x[it][m] = ldg_stream_f2(src + (long)(UPI * it + S0 * m) * n2);
       }
       mbar_wait(&tbar, 0);
 #pragma unroll
@@ -91,20 +114,23 @@ __global__ void __launch_bounds__(288, 2) fwd_cols_v2(Pass1Args const a, ColsV2T
         int const j = ul + UPI * it;
         Dft<R0, false>::run(x[it]);
         float2 w[R0];
-        load_stage_twiddles<R0, S0>(s_tw, j, w);
+        if (TWL) {
+#pragma unroll
+          for (int t = 1; t < R0; t++) w[t] = s_tw[(t - 1) * S0 + j];
+        } else
+          load_stage_twiddles<R0, S0>(s_tw, j, w);
         float2 *d = mycol + j;
         d[0] = x[it][0];
 #pragma unroll
         for (int t = 1; t < R0; t++) d[t * S0] = cmul(x[it][t], w[t]);
       }
     } else {
-      int const *src = reinterpret_cast<int const *>(a.in) + (long)blk * a.hop + n2g;
+      int const *src = reinterpret_cast<int const *>(a.in) + (long)blk * a.hop + n2g + (long)ul * n2;
       int raw[3][R0];
 #pragma unroll
       for (int it = 0; it < 3; it++) {
-        int const *p = src + (long)(ul + UPI * it) * a.n2;
 #pragma unroll
-        for (int m = 0; m < R0; m++) raw[it][m] = ldg_stream_b32(p + m * rstep);
+        for (int m = 0; m < R0; m++) raw[it][m] = ldg_stream_b32(src + (long)(UPI * it + S0 * m) * n2);
       }
       mbar_wait(&tbar, 0);
 #pragma unroll
@@ -119,16 +145,20 @@ __global__ void __launch_bounds__(288, 2) fwd_cols_v2(Pass1Args const a, ColsV2T
               lo ^= (short)((lo & 1) ? 0xfffe : 0);
               hi ^= (short)((hi & 1) ? 0xfffe : 0);
             }
-            if (a.stats && (long)(j + S0 * m) * a.n2 + n2g >= a.first_new) {
+            if (a.stats && (long)(j + S0 * m) * n2 + n2g >= a.first_new) {
               energy += (unsigned long long)((int)lo * lo) + (unsigned long long)((int)hi * hi);
               clips += (lo > 32766 || lo < -32766) + (hi > 32766 || hi < -32766);
             }
           }
-          x[m] = make_float2((float)lo * sc, (float)hi * sc);
+          x[m] = make_float2((float)lo, (float)hi);  // the int16 scale rides on the inter-pass twiddle
         }
         Dft<R0, false>::run(x);
         float2 w[R0];
-        load_stage_twiddles<R0, S0>(s_tw, j, w);
+        if (TWL) {
+#pragma unroll
+          for (int t = 1; t < R0; t++) w[t] = s_tw[(t - 1) * S0 + j];
+        } else
+          load_stage_twiddles<R0, S0>(s_tw, j, w);
         float2 *d = mycol + j;
         d[0] = x[0];
 #pragma unroll
@@ -150,19 +180,21 @@ __global__ void __launch_bounds__(288, 2) fwd_cols_v2(Pass1Args const a, ColsV2T
     }
   }
   __syncthreads();
+  if (dbg && tid == 0) dbg[1] = gtimer();
 
   // ---- stage 1 in shared memory: 12 blocks of 108, stride 9 -----------------------------------
   if (col_ok) {
     float2 const *tw1 = s_tw + P::tw_off(1);
+    // j = u mod 9 with u = ul + 36 it: the same for the three butterflies -> twiddles formed once
+    int const b0 = ul / S1, j = ul - b0 * S1;
+    float2 w[R1];
+    load_stage_twiddles<R1, S1>(tw1, j, w);
 #pragma unroll 1
     for (int it = 0; it < 3; it++) {
-      int const u = ul + UPI * it;
-      int const b = u / S1, j = u - b * S1;
-      float2 *p = mycol + b * NSUB1 + j;
-      float2 x[R1], w[R1];
+      float2 *p = mycol + (b0 + (UPI / S1) * it) * NSUB1 + j;
+      float2 x[R1];
 #pragma unroll
       for (int m = 0; m < R1; m++) x[m] = p[m * S1];
-      load_stage_twiddles<R1, S1>(tw1, j, w);
       Dft<R1, false>::run(x);
       p[0] = x[0];
 #pragma unroll
@@ -170,28 +202,31 @@ __global__ void __launch_bounds__(288, 2) fwd_cols_v2(Pass1Args const a, ColsV2T
     }
   }
   __syncthreads();
+  if (dbg && tid == 0) dbg[2] = gtimer();
 
   // ---- stage 2 fused with the store: X[k1] * W_nc^{n2 k1} -> mid[k1][n2] ------------------------
   if (col_ok) {
     float2 wT[R2];
 #pragma unroll
     for (int t = 0; t < R2; t++) wT[t] = s_twT[c * 9 + t];
-    float2 *dst = a.mid + (long)blk * a.nc + n2g;
+    // u = ul + 36 it = t0*12 + t1 -> k1 = kbase + 144 t2 with kbase = t0 + 12 t1 = kbase(ul) + 3 it
+    int const kb0 = ul / 12 + 12 * (ul % 12);
+    float2 *dst = a.mid + (long)mblk * nc + n2g + (long)kb0 * n2;
+    float const os = a.out_scale;
 #pragma unroll
     for (int it = 0; it < 4; it++) {
-      int const u = ul + UPI * it;        // = t0*12 + t1
-      int const t0 = u / 12, t1 = u - t0 * 12;
-      int const kbase = t0 + 12 * t1;     // k1 = kbase + 144*t2
+      int const u = ul + UPI * it;
       float2 const *p = mycol + u * R2;
       float2 x[R2];
 #pragma unroll
       for (int m = 0; m < R2; m++) x[m] = p[m];
       Dft<R2, false>::run(x);
-      float2 const wb = twU[it];
+      float2 const wb = make_float2(twU[it].x * os, twU[it].y * os);
 #pragma unroll
-      for (int t = 0; t < R2; t++) dst[(long)(kbase + 144 * t) * a.n2] = cmul(x[t], cmul(wb, wT[t]));
+      for (int t = 0; t < R2; t++) dst[(long)(3 * it + 144 * t) * n2] = cmul(x[t], cmul(wb, wT[t]));
     }
   }
+  if (dbg && tid == 0) dbg[3] = gtimer();
 }
 
 // ------------------------------------------------------------------ pass 2: rows --------------
@@ -199,7 +234,9 @@ __global__ void __launch_bounds__(288, 2) fwd_cols_v2(Pass1Args const a, ColsV2T
 // interleaved over the 8 columns; the radix-5 last stage is fused with the real split: the thread
 // that owns butterfly u of row k1 also takes butterfly 249-u of the mirror row N1-k1, which holds
 // exactly the partners Z[Nc-k] of its five outputs (digit complement: 1249-k2 <-> (9-t0,24-t1,4-t2)).
-template <bool REAL_SPLIT>
+// N1C: row count as a compile-time constant (0 = from the arguments).  HALVED: the 1/2 of the real
+// split was already folded into the column pass (Pass1Args::out_scale).
+template <bool REAL_SPLIT, int N1C = 0, bool HALVED = false>
 __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTables const tb) {
   using P = S1250v2;
   constexpr int N2 = 1250, PITCH = 1250, T = 256;
@@ -215,7 +252,11 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
   constexpr int IPC = REAL_SPLIT ? 4 : 8;
   RowItem const *items = a.items + (long)blockIdx.x * IPC;
   unsigned long long *dbg = a.dbg ? a.dbg + 6 * ((long)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
-  if (dbg && tid == 0) dbg[0] = gtimer();
+  if (dbg && tid == 0) {
+    dbg[0] = gtimer();
+    dbg[5] = sm_id();
+  }
+  int const mblk = a.mid_mod ? blk % a.mid_mod : blk;
   // which global row sits in which tile column
   auto row_of = [&](int col) -> int {
     RowItem const it = items[REAL_SPLIT ? col >> 1 : col];
@@ -232,7 +273,7 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
     mbar_fence_init();
     if (row >= 0) {
       mbar_expect_tx(&bars[warp], N2 * 8);
-      bulk_g2s(tile + warp * PITCH, a.mid + (long)blk * a.nc + (long)row * N2, N2 * 8, &bars[warp]);
+      bulk_g2s(tile + warp * PITCH, a.mid + (long)mblk * a.nc + (long)row * N2, N2 * 8, &bars[warp]);
     }
     if (warp == 0) {
       constexpr uint32_t TWB = (uint32_t)((static_tw_count<P>() + 1) & ~1) * 8u;
@@ -285,7 +326,8 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
   if (dbg && tid == 0) dbg[2] = gtimer();
 
   float2 *spec = a.spec + (long)blk * a.spec_stride;
-  int const n1 = a.n1;
+  int const n1 = N1C ? N1C : a.n1;
+  float const hf = HALVED ? 1.0f : 0.5f;
   if (!REAL_SPLIT) {
     // ---- stage 2 fused with the plain store: X[k1 + n1*k2], k2 = t0 + 10 t1 + 250 t2 ---------
     if (col_ok) {
@@ -299,8 +341,9 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
 #pragma unroll
         for (int m = 0; m < R2; m++) x[m] = p[m];
         Dft<R2, false>::run(x);
+        float2 *d = dst + (long)n1 * kb;
 #pragma unroll
-        for (int t = 0; t < R2; t++) dst[(long)n1 * (kb + 250 * t)] = x[t];
+        for (int t = 0; t < R2; t++) d[(long)n1 * 250 * t] = x[t];
       }
     }
     return;
@@ -309,7 +352,7 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
   // W_N^{n1*k2} = exp(-i*pi*k2/1250); k2 = kb + 250 t2 -> D[kb] * exp(-i*pi*t2/5)
   int const i = tid & 3, uq = tid >> 2;  // item (row pair) 0..3, butterfly lane 0..63
   RowItem const it = items[i];
-  int const nc = (int)a.nc;
+  int const nc = N1C ? N1C * N2 : (int)a.nc;
   if (it.kind == kRowPair) {
     float2 const *ca = tile + (2 * i) * PITCH, *cb = tile + (2 * i + 1) * PITCH;
     float2 const rootC = __ldg(tb.rootC + it.row_a);
@@ -320,6 +363,7 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
       float2 const wkb = cmul(rootC, __ldg(a.rootD + kb));  // W_N^{row_a + n1*kb}
       float2 za[R2], zb[R2];
       float2 const *pa = ca + u * R2, *pb = cb + (N2 / R2 - 1 - u) * R2;
+      float2 *pk = spec + (it.row_a + n1 * kb), *pm = spec + (nc - it.row_a - n1 * kb);  // k = row_a + n1 (kb + 250 t)
 #pragma unroll
       for (int m = 0; m < R2; m++) {
         za[m] = pa[m];
@@ -331,16 +375,16 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
       for (int t = 0; t < R2; t++) {
         float2 const A = za[t], B = zb[R2 - 1 - t];
         float2 const w = (t == 0) ? wkb : cmul(wkb, wroot<10>(t));  // exp(-i*pi*t/5) = W_10^t
-        float2 const E = make_float2(0.5f * (A.x + B.x), 0.5f * (A.y - B.y));
-        float2 const O = make_float2(0.5f * (A.x - B.x), 0.5f * (A.y + B.y));
+        float2 const E = HALVED ? make_float2(A.x + B.x, A.y - B.y) : make_float2(0.5f * (A.x + B.x), 0.5f * (A.y - B.y));
+        float2 const O = HALVED ? make_float2(A.x - B.x, A.y + B.y) : make_float2(0.5f * (A.x - B.x), 0.5f * (A.y + B.y));
         float2 const Pp = cmul(w, O);
-        int const k = it.row_a + n1 * (kb + 250 * t);
-        spec[k] = make_float2(E.x + Pp.y, E.y - Pp.x);          // X[k]    = E - i P
-        spec[nc - k] = make_float2(E.x - Pp.y, -(E.y + Pp.x));  // X[Nc-k] = conj(E + i P)
+        pk[(long)n1 * 250 * t] = make_float2(E.x + Pp.y, E.y - Pp.x);       // X[k]    = E - i P
+        pm[-(long)n1 * 250 * t] = make_float2(E.x - Pp.y, -(E.y + Pp.x));  // X[Nc-k] = conj(E + i P)
       }
     }
   }
   // rows that pair with themselves (k1 = 0 and k1 = n1/2): last stage in place, then the v1 epilogue
+  if (dbg && tid == 0) dbg[3] = gtimer();
   bool const has_self = (items[0].kind == kRowSelf0 || items[0].kind == kRowSelfMid) ||
                         (items[1].kind == kRowSelf0 || items[1].kind == kRowSelfMid) ||
                         (items[2].kind == kRowSelf0 || items[2].kind == kRowSelfMid) ||
@@ -371,8 +415,8 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
       int const k2m = self0 ? (k2 == 0 ? 0 : N2 - k2) : N2 - 1 - k2;
       float2 const A = col[static_slot<P>(k2)], B = col[static_slot<P>(k2m)];
       float2 const w = cmul(rootC, __ldg(a.rootD + k2));
-      float2 const E = make_float2(0.5f * (A.x + B.x), 0.5f * (A.y - B.y));
-      float2 const O = make_float2(0.5f * (A.x - B.x), 0.5f * (A.y + B.y));
+      float2 const E = make_float2(hf * (A.x + B.x), hf * (A.y - B.y));
+      float2 const O = make_float2(hf * (A.x - B.x), hf * (A.y + B.y));
       float2 const Pp = cmul(w, O);
       int const k = its.row_a + n1 * k2;
       spec[k] = make_float2(E.x + Pp.y, E.y - Pp.x);
