@@ -19,6 +19,7 @@
 #include "plan.cuh"
 #include "static_kernels.cuh"
 #include "static_kernels_v2.cuh"
+#include "static_kernels_v3.cuh"
 
 using namespace kfft;
 
@@ -26,9 +27,19 @@ using namespace kfft;
 static thread_local std::string g_err;
 static std::atomic<unsigned long long> g_launches{0};
 
-static std::atomic<int> g_tuning[8];      // experiment knobs (kgpu_set_tuning), 0 = default
+static std::atomic<int> g_tuning[16];
+static int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}      // experiment knobs (kgpu_set_tuning), 0 = default
 extern "C" int kgpu_set_tuning(int key, int value) {
-  if (key < 0 || key >= 8) return -1;
+  if (key < 0 || key >= 16) return -1;
   g_tuning[key].store(value);
   return 0;
 }
@@ -438,12 +449,15 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
                  s2 = sizeof(float2) * ((size_t)kTile * m->pitch2 + static_tw_count<S1250>());
     (void)s14;
     size_t const sv1 = sizeof(float2) * (8 * 1298 + 1288 + 80), sv2 = sizeof(float2) * (8 * 1250 + 1246);
+    size_t const sv3 = sizeof(float2) * (2 * 8 * 1250 + 1246);
     if (set_smem((const void *)fwd_cols_v2<0>, sv1) || set_smem((const void *)fwd_cols_v2<1>, sv1) ||
         set_smem((const void *)fwd_cols_v2<2>, sv1) || set_smem((const void *)fwd_rows_v2<true>, sv2) ||
         set_smem((const void *)fwd_rows_v2<false>, sv2) ||
         set_smem((const void *)fwd_cols_v2<0, 1250>, sv1) || set_smem((const void *)fwd_cols_v2<1, 1250>, sv1) ||
         set_smem((const void *)fwd_cols_v2<2, 1250>, sv1) || set_smem((const void *)fwd_cols_v2<1, 1250, 1>, sv1) ||
-        set_smem((const void *)fwd_rows_v2<true, 1296, true>, sv2) || set_smem((const void *)fwd_rows_v2<false, 1296, false>, sv2) ||
+        set_smem((const void *)fwd_rows_v2<true, 1296, true>, sv2) ||
+        set_smem((const void *)fwd_rows_v3<true, 1296, true>, sv3) || set_smem((const void *)fwd_rows_v3<false, 1296, false>, sv3) ||
+        set_smem((const void *)fwd_rows_v3<true, 0, false>, sv3) || set_smem((const void *)fwd_rows_v3<false, 0, false>, sv3) || set_smem((const void *)fwd_rows_v2<false, 1296, false>, sv2) ||
         set_smem((const void *)fwd_cols_static<0, S1296, 8, 1>, s18) || set_smem((const void *)fwd_cols_static<1, S1296, 8, 1>, s18) ||
         set_smem((const void *)fwd_cols_static<2, S1296, 8, 1>, s18) || set_smem((const void *)fwd_cols_static<0, S1296, 8, 2>, s18) ||
         set_smem((const void *)fwd_cols_static<1, S1296, 8, 2>, s18) || set_smem((const void *)fwd_cols_static<2, S1296, 8, 2>, s18) ||
@@ -614,7 +628,15 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
     ProfScope ps(K_FWD_ROWS, st);
     if (use_static && m->static_rows == 1250 && g_tuning[5].load() != 1) {
       size_t const sv2 = sizeof(float2) * (8 * 1250 + 1246);
-      if (a2.real_split && halved) fwd_rows_v2<true, 1296, true><<<g2, 256, sv2, st>>>(a2, tb);
+      if (g_tuning[8].load() == 1) {  // persistent: one CTA per SM walks over the tiles
+        size_t const sv3 = sizeof(float2) * (2 * 8 * 1250 + 1246);
+        int const ntiles = m->n_item_ctas * nblocks;
+        int const grid = std::min(sm_count(), ntiles);
+        if (a2.real_split && halved) fwd_rows_v3<true, 1296, true><<<grid, 512, sv3, st>>>(a2, tb, m->n_item_ctas, ntiles);
+        else if (a2.real_split) fwd_rows_v3<true, 0, false><<<grid, 512, sv3, st>>>(a2, tb, m->n_item_ctas, ntiles);
+        else if (m->sp.n1 == 1296) fwd_rows_v3<false, 1296, false><<<grid, 512, sv3, st>>>(a2, tb, m->n_item_ctas, ntiles);
+        else fwd_rows_v3<false, 0, false><<<grid, 512, sv3, st>>>(a2, tb, m->n_item_ctas, ntiles);
+      } else if (a2.real_split && halved) fwd_rows_v2<true, 1296, true><<<g2, 256, sv2, st>>>(a2, tb);
       else if (a2.real_split) fwd_rows_v2<true><<<g2, 256, sv2, st>>>(a2, tb);
       else if (m->sp.n1 == 1296) fwd_rows_v2<false, 1296, false><<<g2, 256, sv2, st>>>(a2, tb);
       else fwd_rows_v2<false><<<g2, 256, sv2, st>>>(a2, tb);

@@ -31,6 +31,26 @@ template <int R, int S> __device__ __forceinline__ void load_stage_twiddles(floa
   }
 }
 
+// pass-2 work item p of the list kgpu.cu builds (row 0 | pairs (k1, n1-k1) | row n1/2 | padding),
+// computed instead of loaded: the row fetch of a CTA does not wait for a table read
+__device__ __forceinline__ RowItem row_item(int p, int n1, bool real_split) {
+  RowItem it;
+  it.pad = 0;
+  if (!real_split) {
+    it.kind = p < n1 ? kRowPlain : kRowEmpty;
+    it.row_a = p;
+    it.row_b = 0;
+    return it;
+  }
+  it.row_a = p;
+  it.row_b = n1 - p;
+  if (p == 0) it.kind = kRowSelf0, it.row_b = 0;
+  else if (2 * p < n1) it.kind = kRowPair;
+  else if (2 * p == n1) it.kind = kRowSelfMid, it.row_b = p;
+  else it.kind = kRowEmpty, it.row_a = it.row_b = 0;
+  return it;
+}
+
 struct ColsV2Tables {
   float2 const *twU;  // [n2][144]  W_nc^{n2 * kbase(u)}, kbase(u) = u/12 + 12*(u%12)   (u = t0*12 + t1)
   float2 const *twT;  // [n2][9]    W_nc^{n2 * 144 * t2}
@@ -250,7 +270,8 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
   int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   int const blk = blockIdx.y;
   constexpr int IPC = REAL_SPLIT ? 4 : 8;
-  RowItem const *items = a.items + (long)blockIdx.x * IPC;
+  int const n1 = N1C ? N1C : a.n1;
+  int const item0 = blockIdx.x * IPC;
   unsigned long long *dbg = a.dbg ? a.dbg + 6 * ((long)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
   if (dbg && tid == 0) {
     dbg[0] = gtimer();
@@ -259,7 +280,7 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
   int const mblk = a.mid_mod ? blk % a.mid_mod : blk;
   // which global row sits in which tile column
   auto row_of = [&](int col) -> int {
-    RowItem const it = items[REAL_SPLIT ? col >> 1 : col];
+    RowItem const it = row_item(item0 + (REAL_SPLIT ? col >> 1 : col), n1, REAL_SPLIT);
     if (REAL_SPLIT) {
       if ((col & 1) == 0) return it.kind != kRowEmpty ? it.row_a : -1;
       return it.kind == kRowPair ? it.row_b : -1;
@@ -322,11 +343,25 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
       for (int t = 0; t < R1; t++) p[t * S1] = x[t];
     }
   }
-  __syncthreads();
+  // REAL: table factors of this thread's four split butterflies, requested before the barrier
+  int const i = tid & 3, uq = tid >> 2;  // item (row pair) 0..3, butterfly lane 0..63
+  RowItem const it = row_item(item0 + i, n1, REAL_SPLIT);
+  float2 rootC = make_float2(1.f, 0.f), rd[4];
+  bool self_item = false;
+  if (REAL_SPLIT) {
+    self_item = it.kind == kRowSelf0 || it.kind == kRowSelfMid;
+    if (it.kind == kRowPair) rootC = __ldg(tb.rootC + it.row_a);
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      int const u = uq + (T / 4) * q;
+      int const t0 = u / 25, t1 = u - t0 * 25;
+      rd[q] = (it.kind == kRowPair && u < N2 / R2) ? __ldg(a.rootD + t0 + 10 * t1) : make_float2(1.f, 0.f);
+    }
+  }
+  int const has_self = __syncthreads_or(self_item);
   if (dbg && tid == 0) dbg[2] = gtimer();
 
   float2 *spec = a.spec + (long)blk * a.spec_stride;
-  int const n1 = N1C ? N1C : a.n1;
   float const hf = HALVED ? 1.0f : 0.5f;
   if (!REAL_SPLIT) {
     // ---- stage 2 fused with the plain store: X[k1 + n1*k2], k2 = t0 + 10 t1 + 250 t2 ---------
@@ -350,17 +385,16 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
   }
   // ---- stage 2 fused with the real split -----------------------------------------------------
   // W_N^{n1*k2} = exp(-i*pi*k2/1250); k2 = kb + 250 t2 -> D[kb] * exp(-i*pi*t2/5)
-  int const i = tid & 3, uq = tid >> 2;  // item (row pair) 0..3, butterfly lane 0..63
-  RowItem const it = items[i];
   int const nc = N1C ? N1C * N2 : (int)a.nc;
   if (it.kind == kRowPair) {
     float2 const *ca = tile + (2 * i) * PITCH, *cb = tile + (2 * i + 1) * PITCH;
-    float2 const rootC = __ldg(tb.rootC + it.row_a);
-#pragma unroll 2
-    for (int u = uq; u < N2 / R2; u += T / 4) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      int const u = uq + (T / 4) * q;
+      if (u >= N2 / R2) break;
       int const t0 = u / 25, t1 = u - t0 * 25;
       int const kb = t0 + 10 * t1;
-      float2 const wkb = cmul(rootC, __ldg(a.rootD + kb));  // W_N^{row_a + n1*kb}
+      float2 const wkb = cmul(rootC, rd[q]);  // W_N^{row_a + n1*kb}
       float2 za[R2], zb[R2];
       float2 const *pa = ca + u * R2, *pb = cb + (N2 / R2 - 1 - u) * R2;
       float2 *pk = spec + (it.row_a + n1 * kb), *pm = spec + (nc - it.row_a - n1 * kb);  // k = row_a + n1 (kb + 250 t)
@@ -385,13 +419,9 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
   }
   // rows that pair with themselves (k1 = 0 and k1 = n1/2): last stage in place, then the v1 epilogue
   if (dbg && tid == 0) dbg[3] = gtimer();
-  bool const has_self = (items[0].kind == kRowSelf0 || items[0].kind == kRowSelfMid) ||
-                        (items[1].kind == kRowSelf0 || items[1].kind == kRowSelfMid) ||
-                        (items[2].kind == kRowSelf0 || items[2].kind == kRowSelfMid) ||
-                        (items[3].kind == kRowSelf0 || items[3].kind == kRowSelfMid);
   if (!has_self) return;  // CTA-uniform
   for (int s = 0; s < 4; s++) {
-    RowItem const its = items[s];
+    RowItem const its = row_item(item0 + s, n1, true);
     if (its.kind != kRowSelf0 && its.kind != kRowSelfMid) continue;
     float2 *col = tile + (2 * s) * PITCH;
     for (int u = tid; u < N2 / R2; u += T) {
@@ -405,16 +435,16 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
   }
   __syncthreads();
   for (int s = 0; s < 4; s++) {
-    RowItem const its = items[s];
+    RowItem const its = row_item(item0 + s, n1, true);
     if (its.kind != kRowSelf0 && its.kind != kRowSelfMid) continue;
     float2 const *col = tile + (2 * s) * PITCH;
-    float2 const rootC = __ldg(tb.rootC + its.row_a);
+    float2 const rC = __ldg(tb.rootC + its.row_a);
     bool const self0 = its.kind == kRowSelf0;
     int const kend = self0 ? N2 / 2 + 1 : (N2 + 1) / 2;
     for (int k2 = tid; k2 < kend; k2 += T) {
       int const k2m = self0 ? (k2 == 0 ? 0 : N2 - k2) : N2 - 1 - k2;
       float2 const A = col[static_slot<P>(k2)], B = col[static_slot<P>(k2m)];
-      float2 const w = cmul(rootC, __ldg(a.rootD + k2));
+      float2 const w = cmul(rC, __ldg(a.rootD + k2));
       float2 const E = make_float2(hf * (A.x + B.x), hf * (A.y - B.y));
       float2 const O = make_float2(hf * (A.x - B.x), hf * (A.y + B.y));
       float2 const Pp = cmul(w, O);

@@ -1,0 +1,243 @@
+// static_kernels_v3.cuh -- persistent forward passes.
+//
+// The per-CTA timeline of the v2 kernels (tools/phase_trace.py) shows each 8-row / 8-column tile
+// waiting 2.3-2.8 us (rows, TMA) or ~3 us (columns, gather) for its input before a single
+// butterfly issues, and with two CTAs per SM about half of the time only one of them is past that
+// wait.  Here one CTA stays on each SM and walks over the tiles:
+//   rows  : 512 threads, two 80 kB tile buffers; the rows of tile k+1 arrive by TMA while tile k
+//           is being transformed, so all 16 warps always have butterflies to issue; the stage
+//           twiddles, barriers and row-item decoding are set up once per CTA instead of per tile.
+#pragma once
+#include "static_kernels_v2.cuh"
+
+namespace kfft {
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------ pass 2: rows, persistent ---
+template <bool REAL_SPLIT, int N1C = 0, bool HALVED = false>
+__global__ void __launch_bounds__(512, 1) fwd_rows_v3(Pass2Args const a, FwdTables const tb, int tiles_per_block, int ntiles) {
+  using P = S1250v2;
+  constexpr int N2 = 1250, PITCH = 1250, T = 512, LPC = T / 8 /*lanes per column*/;
+  constexpr int R0 = 10, S0 = 125, R1 = 25, NSUB1 = 125, S1 = 5, R2 = 5;
+  constexpr int IPC = REAL_SPLIT ? 4 : 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *bufs = reinterpret_cast<float2 *>(smem_raw);  // [2][8][PITCH]
+  float2 *s_tw = bufs + 2 * 8 * PITCH;
+  __shared__ __align__(16) RowItem s_items[2][8];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) uint64_t tbar;
+  TilePlan const &pl = c_plans[a.plan];
+  int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int const n1 = N1C ? N1C : a.n1;
+  int const nc = N1C ? N1C * N2 : (int)a.nc;
+  int const G = gridDim.x;
+
+  // warp 0: fetch the rows of tile t into buffer b (lanes 0..7 = tile columns)
+  auto issue = [&](int t, int b) {
+    int const blk = t / tiles_per_block, x = t - blk * tiles_per_block;
+    int const mblk = a.mid_mod ? blk % a.mid_mod : blk;
+    RowItem it;
+    it.kind = kRowEmpty;
+    it.row_a = it.row_b = it.pad = 0;
+    if (lane < IPC) {
+      it = row_item(x * IPC + lane, n1, REAL_SPLIT);
+      s_items[b][lane] = it;
+    }
+    int const src = REAL_SPLIT ? (lane >> 1) & 3 : lane & 7;
+    int const kind = __shfl_sync(0xffffffffu, it.kind, src);
+    int const ra = __shfl_sync(0xffffffffu, it.row_a, src), rb = __shfl_sync(0xffffffffu, it.row_b, src);
+    if (lane < 8) {
+      int row;
+      if (REAL_SPLIT)
+        row = (lane & 1) == 0 ? (kind != kRowEmpty ? ra : -1) : (kind == kRowPair ? rb : -1);
+      else
+        row = kind == kRowPlain ? ra : -1;
+      if (row >= 0) {
+        mbar_expect_tx(&bars[b], N2 * 8);
+        bulk_g2s(bufs + (b * 8 + lane) * PITCH, a.mid + (long)mblk * nc + (long)row * N2, N2 * 8, &bars[b]);
+      } else
+        mbar_arrive(&bars[b]);
+    }
+  };
+
+  if (tid == 0) {
+    mbar_init(&bars[0], 8);
+    mbar_init(&bars[1], 8);
+    mbar_init(&tbar, 1);
+    mbar_fence_init();
+    constexpr uint32_t TWB = (uint32_t)((static_tw_count<P>() + 1) & ~1) * 8u;
+    mbar_expect_tx(&tbar, TWB);
+    bulk_g2s(s_tw, pl.tw, TWB, &tbar);
+  }
+  __syncthreads();
+  if (warp == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  mbar_wait(&tbar, 0);
+
+  int const c = tid & 7, ul = tid >> 3;  // column, butterfly lane 0..63
+  float2 const *tw1 = s_tw + P::tw_off(1);
+  int k = 0;
+  for (int t = blockIdx.x; t < ntiles; t += G, k++) {
+    int const b = k & 1;
+    if (warp == 0 && t + G < ntiles) {  // buffer b^1 was released by the barrier that ended tile k-1
+      fence_proxy_async();
+      issue(t + G, b ^ 1);
+    }
+    mbar_wait(&bars[b], (k >> 1) & 1);
+    int const blk = t / tiles_per_block;
+    float2 *tile = bufs + b * 8 * PITCH;
+    RowItem const itc = s_items[b][REAL_SPLIT ? c >> 1 : c];
+    bool col_ok;
+    if (REAL_SPLIT)
+      col_ok = (c & 1) == 0 ? itc.kind != kRowEmpty : itc.kind == kRowPair;
+    else
+      col_ok = itc.kind == kRowPlain;
+    float2 *mycol = tile + c * PITCH;
+
+    // ---- stage 0: radix 10, stride 125 (125 butterflies per column, 64 lanes) -------------------
+    if (col_ok) {
+#pragma unroll
+      for (int jj = 0; jj < 2; jj++) {
+        int const j = ul + LPC * jj;
+        if (j < S0) {
+          float2 *p = mycol + j;
+          float2 x[R0], w[R0];
+#pragma unroll
+          for (int m = 0; m < R0; m++) x[m] = p[m * S0];
+          load_stage_twiddles<R0, S0>(s_tw, j, w);
+          Dft<R0, false>::run(x);
+          p[0] = x[0];
+#pragma unroll
+          for (int t2 = 1; t2 < R0; t2++) p[t2 * S0] = cmul(x[t2], w[t2]);
+        }
+      }
+    }
+    __syncthreads();
+    // ---- stage 1: radix 25, 10 blocks of 125, stride 5 (50 butterflies per column) ---------------
+    if (col_ok && ul < N2 / R1) {
+      int const bb = ul / S1, j = ul - bb * S1;
+      float2 *p = mycol + bb * NSUB1 + j;
+      float2 x[R1];
+#pragma unroll
+      for (int m = 0; m < R1; m++) x[m] = p[m * S1];
+      Dft<R1, false>::run(x);
+#pragma unroll
+      for (int t2 = 1; t2 < R1; t2++) x[t2] = cmul(x[t2], tw1[(t2 - 1) * S1 + j]);
+#pragma unroll
+      for (int t2 = 0; t2 < R1; t2++) p[t2 * S1] = x[t2];
+    }
+
+    float2 *spec = a.spec + (long)blk * a.spec_stride;
+    if (!REAL_SPLIT) {
+      __syncthreads();
+      // ---- stage 2 fused with the plain store: X[k1 + n1*k2], k2 = t0 + 10 t1 + 250 t2 ---------
+      if (col_ok) {
+        float2 *dst = spec + itc.row_a;
+#pragma unroll 2
+        for (int u = ul; u < N2 / R2; u += LPC) {
+          int const t0 = u / 25, t1 = u - t0 * 25;
+          int const kb = t0 + 10 * t1;
+          float2 const *p = mycol + u * R2;
+          float2 x[R2];
+#pragma unroll
+          for (int m = 0; m < R2; m++) x[m] = p[m];
+          Dft<R2, false>::run(x);
+          float2 *d = dst + (long)n1 * kb;
+#pragma unroll
+          for (int t2 = 0; t2 < R2; t2++) d[(long)n1 * 250 * t2] = x[t2];
+        }
+      }
+      __syncthreads();  // tile buffer free again
+      continue;
+    }
+    // ---- stage 2 fused with the real split -----------------------------------------------------
+    // W_N^{n1*k2} = exp(-i*pi*k2/1250); k2 = kb + 250 t2 -> D[kb] * exp(-i*pi*t2/5)
+    int const i = tid & 3, uq = tid >> 2;  // item (row pair) 0..3, butterfly lane 0..127
+    RowItem const it = s_items[b][i];
+    bool const self_item = it.kind == kRowSelf0 || it.kind == kRowSelfMid;
+    // table factors of this thread's two butterflies: requested before the barrier, used after it
+    float2 rootC = make_float2(1.f, 0.f), rd[2];
+    if (it.kind == kRowPair) rootC = __ldg(tb.rootC + it.row_a);
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      int const u = uq + (T / 4) * q;
+      int const t0 = u / 25, t1 = u - t0 * 25;
+      rd[q] = (it.kind == kRowPair && u < N2 / R2) ? __ldg(a.rootD + t0 + 10 * t1) : make_float2(1.f, 0.f);
+    }
+    int const has_self = __syncthreads_or(self_item);
+    if (it.kind == kRowPair) {
+      float2 const *ca = tile + (2 * i) * PITCH, *cb = tile + (2 * i + 1) * PITCH;
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        int const u = uq + (T / 4) * q;
+        if (u < N2 / R2) {
+          int const t0 = u / 25, t1 = u - t0 * 25;
+          int const kb = t0 + 10 * t1;
+          float2 const wkb = cmul(rootC, rd[q]);  // W_N^{row_a + n1*kb}
+          float2 za[R2], zb[R2];
+          float2 const *pa = ca + u * R2, *pb = cb + (N2 / R2 - 1 - u) * R2;
+          float2 *pk = spec + (it.row_a + n1 * kb), *pm = spec + (nc - it.row_a - n1 * kb);  // k = row_a + n1 (kb + 250 t)
+#pragma unroll
+          for (int m = 0; m < R2; m++) {
+            za[m] = pa[m];
+            zb[m] = pb[m];
+          }
+          Dft<R2, false>::run(za);
+          Dft<R2, false>::run(zb);
+#pragma unroll
+          for (int t2 = 0; t2 < R2; t2++) {
+            float2 const A = za[t2], B = zb[R2 - 1 - t2];
+            float2 const w = (t2 == 0) ? wkb : cmul(wkb, wroot<10>(t2));  // exp(-i*pi*t/5) = W_10^t
+            float2 const E = HALVED ? make_float2(A.x + B.x, A.y - B.y) : make_float2(0.5f * (A.x + B.x), 0.5f * (A.y - B.y));
+            float2 const O = HALVED ? make_float2(A.x - B.x, A.y + B.y) : make_float2(0.5f * (A.x - B.x), 0.5f * (A.y + B.y));
+            float2 const Pp = cmul(w, O);
+            pk[(long)n1 * 250 * t2] = make_float2(E.x + Pp.y, E.y - Pp.x);       // X[k]    = E - i P
+            pm[-(long)n1 * 250 * t2] = make_float2(E.x - Pp.y, -(E.y + Pp.x));  // X[Nc-k] = conj(E + i P)
+          }
+        }
+      }
+    }
+    if (has_self) {  // CTA-uniform: rows that pair with themselves (k1 = 0 and k1 = n1/2)
+      float const hf = HALVED ? 1.0f : 0.5f;
+      for (int s = 0; s < 4; s++) {
+        RowItem const its = s_items[b][s];
+        if (its.kind != kRowSelf0 && its.kind != kRowSelfMid) continue;
+        float2 *col = tile + (2 * s) * PITCH;
+        for (int u = tid; u < N2 / R2; u += T) {
+          float2 x[R2];
+#pragma unroll
+          for (int m = 0; m < R2; m++) x[m] = col[u * R2 + m];
+          Dft<R2, false>::run(x);
+#pragma unroll
+          for (int m = 0; m < R2; m++) col[u * R2 + m] = x[m];
+        }
+      }
+      __syncthreads();
+      for (int s = 0; s < 4; s++) {
+        RowItem const its = s_items[b][s];
+        if (its.kind != kRowSelf0 && its.kind != kRowSelfMid) continue;
+        float2 const *col = tile + (2 * s) * PITCH;
+        float2 const rC = __ldg(tb.rootC + its.row_a);
+        bool const self0 = its.kind == kRowSelf0;
+        int const kend = self0 ? N2 / 2 + 1 : (N2 + 1) / 2;
+        for (int k2 = tid; k2 < kend; k2 += T) {
+          int const k2m = self0 ? (k2 == 0 ? 0 : N2 - k2) : N2 - 1 - k2;
+          float2 const A = col[static_slot<P>(k2)], B = col[static_slot<P>(k2m)];
+          float2 const w = cmul(rC, __ldg(a.rootD + k2));
+          float2 const E = make_float2(hf * (A.x + B.x), hf * (A.y - B.y));
+          float2 const O = make_float2(hf * (A.x - B.x), hf * (A.y + B.y));
+          float2 const Pp = cmul(w, O);
+          int const kk = its.row_a + n1 * k2;
+          spec[kk] = make_float2(E.x + Pp.y, E.y - Pp.x);
+          if (nc - kk != kk) spec[nc - kk] = make_float2(E.x - Pp.y, -(E.y + Pp.x));
+        }
+      }
+    }
+    __syncthreads();  // tile buffer free again
+  }
+}
+
+}  // namespace kfft

@@ -1,0 +1,34 @@
+#!/usr/bin/env python3
+"""Compare the spectra of two kernel variants on the same input (cfg-2 sizes, REAL int16 and COMPLEX float).
+usage: ab_check.py "8=1" ["9=1" ...]   (each variant is compared with the default)"""
+import sys
+from pathlib import Path
+import numpy as np, torch
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import bench
+from ka9q_radio_b200 import capi
+from ka9q_radio_b200.channelizer import Channelizer
+lib = capi.load(); dev = torch.device("cuda:0")
+def setv(v):
+    for k in range(16): lib.kgpu_set_tuning(k, 0)
+    for kv in v.split(","):
+        if kv and kv != "default":
+            k, val = kv.split("="); lib.kgpu_set_tuning(int(k), int(val))
+B = 5
+rng = np.random.default_rng(1)
+for name, in_type, L, M in (("real-i16", capi.KGPU_REAL, bench.L, bench.M), ("complex-f32", capi.KGPU_COMPLEX, bench.L // 2, (bench.M - 1) // 2 + 1)):
+    cz = Channelizer(L, M, in_type, dev, capacity=4)
+    if in_type == capi.KGPU_REAL:
+        x = rng.integers(-3000, 3000, B * L, dtype=np.int16)
+    else:
+        x = (rng.standard_normal(B * L) + 1j * rng.standard_normal(B * L)).astype(np.complex64)
+    d = cz.stage_stream(x)
+    ref = cz.alloc_spectra(B); setv("default"); cz.forward(d, B, ref, scale=bench.SCALE); torch.cuda.synchronize()
+    print(name, cz.master.describe())
+    for v in sys.argv[1:]:
+        out = cz.alloc_spectra(B); out.zero_(); setv(v); cz.forward(d, B, out, scale=bench.SCALE); torch.cuda.synchronize()
+        nb = cz.master.bins
+        diff = (out[:, :nb] - ref[:, :nb]).abs().max().item(); mag = ref[:, :nb].abs().max().item()
+        print("  variant %-10s max|diff| %.3e  rel %.3e  %s" % (v, diff, diff / mag, "OK" if diff / mag < 1e-6 else "MISMATCH"))
+    setv("default"); cz.close()

@@ -34,7 +34,7 @@ spec, out = cz.alloc_spectra(B), cz.alloc_outputs(B)
 ng = nstream // B
 def apply(v):
     lib.kgpu_use_static_kernels(1)
-    for k in range(8): lib.kgpu_set_tuning(k, 0)
+    for k in range(16): lib.kgpu_set_tuning(k, 0)
     for kv in v.split(","):
         if not kv or kv == "default": continue
         k, val = kv.split("=")
