@@ -202,7 +202,22 @@ def run_ours(args) -> None:
     spec = spec2[0]
     out = cz.alloc_outputs(B)
     comp = torch.cuda.current_stream(dev)
-    if args.mg_mode == "spectrum" or world == 1:
+    mc, mc_why = None, "single GPU"
+    if world > 1 and args.mg_mode == "spectrum-mc":
+        # own multicast copy kernel over NVSwitch when the fabric offers a multicast mapping
+        from ka9q_radio_b200.multicast import SpectrumMulticast
+        mc, mc_why = SpectrumMulticast.create(rank, world, dev, 2, B * cz.master.spec_stride * 2,
+                                                  nctas=int(os.environ.get("KA9Q_MC_CTAS", "64")))
+    if mc is not None:
+        from ka9q_radio_b200.sharding import MulticastSharder
+        symm2 = [mc.slot_view(s, (B, cz.master.spec_stride)) for s in range(2)]
+        sharder = MulticastSharder(
+            rank, world,
+            forward=lambda step, slot: cz.forward(d_stream, B, spec2[slot], scale=SCALE, first_block=(step % ngroups) * B),
+            push=lambda slot: mc.push(slot, spec2[slot]),
+            ready=mc.ready, arrive=mc.arrive,
+            channels=lambda step, slot: cz.channels(spec2[slot] if rank == 0 else symm2[slot], B, out))
+    elif args.mg_mode in ("spectrum", "spectrum-mc") or world == 1:
         # north_star: forward transform once (rank 0), ONE broadcast of the block spectra per step
         sharder = PipelinedSharder(
             rank, world,
@@ -224,7 +239,7 @@ def run_ours(args) -> None:
             cz.channels(spec2[slot], B, out)
 
         sharder = PipelinedSharder(rank, world, forward=stage,
-                                   broadcast=lambda slot: dist.broadcast(win2[slot], src=0, async_op=True),
+                                   broadcast=lambda slot: dist.broadcast(win2[slot].view(torch.uint8), src=0, async_op=True),
                                    channels=chan_after_forward)
 
     def barrier():
@@ -327,8 +342,12 @@ def run_ours(args) -> None:
                    "l2_policy": "input stream larger than L2 (126 MB), consecutive groups cycled; no explicit flush",
                    "plan": cz.master.describe(),
                    "parallelism": ("single GPU" if world == 1 else
-                                   (f"{world} GPUs: forward on rank 0, 1 NCCL broadcast of the spectrum per step, "
-                                    if args.mg_mode == "spectrum" else
+                                   (f"{world} GPUs: forward on rank 0, spectra stored once per step to an NVSwitch multicast "
+                                    "address by kgpu_multicast_copy (own kernel, multimem.st) + symmetric-memory barrier, "
+                                    if mc is not None else
+                                    f"{world} GPUs: forward on rank 0, 1 NCCL broadcast of the spectrum per step"
+                                    + (f" (multicast path unavailable: {mc_why}), " if args.mg_mode == "spectrum-mc" else ", ")
+                                    if args.mg_mode in ("spectrum", "spectrum-mc") else
                                     f"{world} GPUs: 1 NCCL broadcast of the int16 window per step, forward replicated, ")
                                    + f"{NCHAN} channels per GPU; value = stream rate x GPUs"),
                    "stream_msps": stream_msps, "realtime_factor": stream_msps / 129.6},
@@ -424,8 +443,10 @@ def main():
     ap.add_argument("--stream-blocks", type=int, default=64, help="resident input stream length (blocks)")
     ap.add_argument("--ref-blocks", type=int, default=12, help="blocks per step of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mg-mode", default="spectrum", choices=["spectrum", "input"],
-                    help="multi-GPU: broadcast the forward spectrum (north_star, default) or the raw input window")
+    ap.add_argument("--mg-mode", default="spectrum", choices=["spectrum", "spectrum-mc", "input"],
+                    help="multi-GPU hand-off: NCCL broadcast of the forward spectrum (north_star, default); the same through this "
+                         "repository's NVSwitch-multicast copy kernel; or NCCL broadcast of the raw input window with the "
+                         "forward transform replicated")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -128,6 +128,14 @@ int kgpu_set_debug_buffer_rows(void *d_buf); /* same for the rows kernel */
 int kgpu_plan_radices(int len, int *radices, int max);
 int kgpu_plan_split(long n, int *n1, int *n2);
 
+/* Multi-GPU hand-off of the block spectra (replaces the per-block multicast the
+ * reference leaves to the network, multicast.c): copy `bytes` (multiple of 16) from this GPU's
+ * `d_src` to `mc_dst`, an NVSwitch MULTICAST address that maps the same symmetric buffer on every
+ * GPU of the group (obtained by the caller, e.g. torch symmetric memory), with multimem.st -- one
+ * NVLink egress serves all peers.  `nctas` thread blocks of 256 threads (0 = default) so the copy
+ * co-resides with the forward kernels of the next step. */
+int kgpu_multicast_copy(const void *d_src, void *mc_dst, unsigned long long bytes, int nctas, void *stream);
+
 /* Algorithmic bytes per block of one forward + all enabled channels. */
 double kgpu_algorithmic_bytes(kgpu_master const *m, kgpu_bank const *b, int fmt);
 

@@ -84,6 +84,7 @@ def load() -> C.CDLL:
     L.kgpu_profile_get.argtypes = [i, vp, vp]
     L.kgpu_plan_radices.argtypes = [i, vp, i]
     L.kgpu_plan_split.argtypes = [l, vp, vp]
+    L.kgpu_multicast_copy.argtypes = [vp, vp, C.c_ulonglong, i, vp]
     L.kgpu_algorithmic_bytes.argtypes = [vp, vp, i]
     L.kgpu_algorithmic_bytes.restype = d
     _lib = L

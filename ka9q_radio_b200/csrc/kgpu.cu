@@ -163,6 +163,45 @@ extern "C" int kgpu_profile_get(int kid, double *total_ms, long *count) {
 
 extern "C" const char *kgpu_last_error(void) { return g_err.c_str(); }
 extern "C" unsigned long long kgpu_launch_count(void) { return g_launches.load(); }
+// ---- spectrum hand-off over NVSwitch multicast ---------------------------------------------------
+// Streaming copy local HBM -> multicast address: 16-byte no-allocate loads, multimem.st stores (the
+// switch replicates each store to every GPU bound to the multicast object).  256 threads and <= 32
+// registers per CTA so that the CTAs fit beside two resident forward CTAs on an SM.
+__global__ void __launch_bounds__(256) mc_push_kernel(float4 const *__restrict__ src, float4 *mc_dst, size_t n16) {
+  size_t const stride = (size_t)gridDim.x * 256;
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  for (; i + 3 * stride < n16; i += 4 * stride) {
+    float4 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(v[q].x), "=f"(v[q].y), "=f"(v[q].z), "=f"(v[q].w)
+                   : "l"(src + i + q * stride));
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+      asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc_dst + i + q * stride), "f"(v[q].x),
+                   "f"(v[q].y), "f"(v[q].z), "f"(v[q].w)
+                   : "memory");
+  }
+  for (; i < n16; i += stride) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src + i));
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc_dst + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+  }
+  __threadfence_system();  // this thread's multicast stores are performed system-wide before the kernel retires
+}
+extern "C" int kgpu_multicast_copy(const void *d_src, void *mc_dst, unsigned long long bytes, int nctas, void *stream) {
+  if (!d_src || !mc_dst || (bytes & 15) || ((uintptr_t)d_src & 15) || ((uintptr_t)mc_dst & 15))
+    return fail("kgpu_multicast_copy: pointers and size must be multiples of 16 bytes");
+  if (bytes == 0) return 0;
+  if (nctas <= 0) nctas = 64;
+  mc_push_kernel<<<nctas, 256, 0, (cudaStream_t)stream>>>((float4 const *)d_src, (float4 *)mc_dst, (size_t)(bytes / 16));
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int kgpu_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;

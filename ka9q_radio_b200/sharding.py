@@ -56,3 +56,53 @@ class PipelinedSharder:
         if handle is not None:
             handle.wait()
         self.channels(step, slot)
+
+
+@dataclass
+class MulticastSharder:
+    """Spectrum hand-off through an NVSwitch multicast mapping instead of a collective call.
+
+    rank 0 keeps its spectra in a private buffer, and after each forward transform its own copy
+    kernel (kgpu_multicast_copy, on a side stream) stores them once to a multicast address that
+    lands in the symmetric buffer of every GPU, followed by the group barrier; the copy overlaps the
+    forward transform of the next step.  The peers enter the same barrier on their compute stream
+    and then run their channel group on their local copy.
+
+    forward(step, slot)    rank 0: fill the private spectrum buffer `slot`
+    push(slot)             rank 0: side stream: wait for forward, copy to multicast, group barrier
+    ready(slot)            rank 0: make the compute stream wait for push(slot) (buffer reusable)
+    arrive(slot)           peers: the group barrier on the compute stream
+    channels(step, slot)   this rank's channel group (rank 0 reads its private buffer)
+
+    Two slots are enough: push(k+2) is ordered behind barrier k+1, which a peer only enters after
+    its channels(k) -- the last reader of the slot that push(k+2) overwrites.
+    """
+
+    rank: int
+    world: int
+    forward: Callable[[int, int], None]
+    push: Callable[[int], None]
+    ready: Callable[[int], None]
+    arrive: Callable[[int], None]
+    channels: Callable[[int, int], None]
+
+    def run(self, steps: Sequence[int]) -> None:
+        prev = None
+        for i, step in enumerate(steps):
+            slot = i % 2
+            if self.rank != 0:
+                self.arrive(slot)
+                self.channels(step, slot)
+                continue
+            self.forward(step, slot)
+            if self.world > 1:
+                self.push(slot)
+            if prev is not None:
+                if self.world > 1:
+                    self.ready(prev[1])
+                self.channels(*prev)
+            prev = (step, slot)
+        if self.rank == 0 and prev is not None:
+            if self.world > 1:
+                self.ready(prev[1])
+            self.channels(*prev)

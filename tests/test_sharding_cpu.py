@@ -54,16 +54,44 @@ def _worker(rank, world, port, tmp):
         for i in mine:
             out[(step, i)] = O.channel_block(O.KO_REAL, X, resp[i], chans[i]["shift"])[-48:].copy()
 
-    PipelinedSharder(rank, world, forward, broadcast, channels).run(range(nsteps))
+    if os.environ.get("KA_SHARDER") == "multicast":
+        # the NVSwitch multicast store + group barrier of bench.py, emulated by a blocking gloo
+        # broadcast: rank 0 keeps private spectra (spec), the peers read the "symmetric" copy (symm)
+        from ka9q_radio_b200.sharding import MulticastSharder
+
+        symm = [torch.zeros(N // 2 + 1, dtype=torch.complex64) for _ in range(2)]
+        log = []
+
+        def push(slot):
+            log.append(("push", slot))
+            symm[slot].copy_(spec[slot])
+            dist.broadcast(symm[slot], src=0)
+
+        def arrive(slot):
+            dist.broadcast(symm[slot], src=0)
+
+        def channels_mc(step, slot):
+            X = (spec if rank == 0 else symm)[slot].numpy()
+            for i in mine:
+                out[(step, i)] = O.channel_block(O.KO_REAL, X, resp[i], chans[i]["shift"])[-48:].copy()
+
+        MulticastSharder(rank, world, forward, push, lambda slot: log.append(("ready", slot)), arrive, channels_mc).run(range(nsteps))
+        if rank == 0:  # every push is acknowledged before its slot's channels and before the slot is refilled
+            assert [e for e in log if e[0] == "push"] == [("push", k % 2) for k in range(nsteps)]
+            assert [e for e in log if e[0] == "ready"] == [("ready", k % 2) for k in range(nsteps)]
+    else:
+        PipelinedSharder(rank, world, forward, broadcast, channels).run(range(nsteps))
     np.save(Path(tmp) / f"rank{rank}.npy", {k: v for k, v in out.items()}, allow_pickle=True)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_gloo_pipeline_matches_single_process(tmp_path, oracle):
+@pytest.mark.parametrize("sharder", ["pipelined", "multicast"])
+def test_two_rank_gloo_pipeline_matches_single_process(tmp_path, oracle, sharder, monkeypatch):
     import torch.multiprocessing as mp
 
-    port = 29600 + (os.getpid() % 300)
+    monkeypatch.setenv("KA_SHARDER", sharder)
+    port = 29600 + (os.getpid() % 300) + (17 if sharder == "multicast" else 0)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     got = {}
     for r in range(2):
