@@ -495,6 +495,7 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
         set_smem((const void *)fwd_cols_v2<0, 1250>, sv1) || set_smem((const void *)fwd_cols_v2<1, 1250>, sv1) ||
         set_smem((const void *)fwd_cols_v2<2, 1250>, sv1) || set_smem((const void *)fwd_cols_v2<1, 1250, 1>, sv1) ||
         set_smem((const void *)fwd_rows_v2<true, 1296, true>, sv2) ||
+        set_smem((const void *)fwd_cols_v3<1, 1250>, sv1) || set_smem((const void *)fwd_cols_v3<2, 1250>, sv1) ||
         set_smem((const void *)fwd_rows_v3<true, 1296, true>, sv3) || set_smem((const void *)fwd_rows_v3<false, 1296, false>, sv3) ||
         set_smem((const void *)fwd_rows_v3<true, 0, false>, sv3) || set_smem((const void *)fwd_rows_v3<false, 0, false>, sv3) || set_smem((const void *)fwd_rows_v2<false, 1296, false>, sv2) ||
         set_smem((const void *)fwd_cols_static<0, S1296, 8, 1>, s18) || set_smem((const void *)fwd_cols_static<1, S1296, 8, 1>, s18) ||
@@ -609,7 +610,12 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
       // folded into the inter-pass twiddle
       halved = (m->in_type == KGPU_REAL) && m->static_rows == 1250;
       a1.out_scale = (fmt == KGPU_FMT_I16 ? scale : 1.0f) * (halved ? 0.5f : 1.0f);
-      if (m->sp.n2 == 1250) {
+      if (m->sp.n2 == 1250 && f != 0 && g_tuning[9].load() == 1) {  // persistent, next tile's words in flight
+        int const tpb = (int)g1.x, ntiles = tpb * nblocks;
+        int const grid = std::min(2 * sm_count(), ntiles);
+        if (f == 1) fwd_cols_v3<1, 1250><<<grid, 288, sv1, st>>>(a1, t2, tpb, ntiles);
+        else fwd_cols_v3<2, 1250><<<grid, 288, sv1, st>>>(a1, t2, tpb, ntiles);
+      } else if (m->sp.n2 == 1250) {
         if (f == 0) fwd_cols_v2<0, 1250><<<g1, 288, sv1, st>>>(a1, t2);
         else if (f == 1 && g_tuning[2].load() == 1) fwd_cols_v2<1, 1250, 1><<<g1, 288, sv1, st>>>(a1, t2);
         else if (f == 1) fwd_cols_v2<1, 1250><<<g1, 288, sv1, st>>>(a1, t2);

@@ -4,6 +4,9 @@
 // waiting 2.3-2.8 us (rows, TMA) or ~3 us (columns, gather) for its input before a single
 // butterfly issues, and with two CTAs per SM about half of the time only one of them is past that
 // wait.  Here one CTA stays on each SM and walks over the tiles:
+//   cols  : 288 threads x 2 CTAs per SM as before, but the 36 raw int16 words a thread needs for the
+//           NEXT tile are requested into the (by then dead) registers right after stage 0 of the
+//           current tile, so the gather latency hides behind stages 1 and 2.
 //   rows  : 512 threads, two 80 kB tile buffers; the rows of tile k+1 arrive by TMA while tile k
 //           is being transformed, so all 16 warps always have butterflies to issue; the stage
 //           twiddles, barriers and row-item decoding are set up once per CTA instead of per tile.
@@ -16,6 +19,152 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+
+// ------------------------------------------------------------------ pass 1: columns, persistent --
+template <int FMT, int N2C>
+__device__ __forceinline__ void cols_v3_request(int (&raw)[3][12], int const *src, int n2) {
+#pragma unroll
+  for (int it = 0; it < 3; it++) {
+#pragma unroll
+    for (int m = 0; m < 12; m++) raw[it][m] = ldg_stream_b32(src + (long)(36 * it + 108 * m) * (N2C ? N2C : n2));
+  }
+}
+
+// int16 formats only (FMT 1, 2): the float format would need 72 look-ahead registers.
+template <int FMT, int N2C = 0>
+__global__ void __launch_bounds__(288, 2) fwd_cols_v3(Pass1Args const a, ColsV2Tables const tb, int tiles_per_block, int ntiles) {
+  static_assert(FMT == 1 || FMT == 2, "int16 input");
+  using P = SPlan<1296, 12, 12, 9>;
+  constexpr int N1 = 1296, PITCH = 1298, T = 288, UPI = T / 8;
+  constexpr int R0 = 12, S0 = 108, R1 = 12, NSUB1 = 108, S1 = 9, R2 = 9;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *tile = reinterpret_cast<float2 *>(smem_raw);  // [8][PITCH]
+  float2 *s_tw = tile + 8 * PITCH;                      // stage twiddles (1287 entries, padded to 1288)
+  float2 *s_twT = s_tw + 1288;                          // [8][9] (padded to 80), per tile
+  __shared__ __align__(8) uint64_t tbar;
+  TilePlan const &pl = c_plans[a.plan];
+  int const tid = threadIdx.x;
+  int const c = tid & 7, ul = tid >> 3;  // column of the tile, butterfly lane 0..35
+  int const n2 = N2C ? N2C : a.n2;
+  long const nc = N2C ? (long)N1 * N2C : a.nc;
+  int const G = gridDim.x;
+  if (tid == 0) {
+    mbar_init(&tbar, 1);
+    mbar_fence_init();
+    mbar_expect_tx(&tbar, 1288 * 8);
+    bulk_g2s(s_tw, pl.tw, 1288 * 8, &tbar);
+  }
+  __syncthreads();
+  float2 *mycol = tile + c * PITCH;
+  float2 const *tw1 = s_tw + P::tw_off(1);
+  int const b0 = ul / S1, j1 = ul - b0 * S1;      // stage-1 butterfly of iteration 0
+  int const kb0 = ul / 12 + 12 * (ul % 12);       // stage-2 output row of iteration 0
+  int const *in = reinterpret_cast<int const *>(a.in);
+
+  int raw[3][R0];
+  int t = blockIdx.x;
+  {
+    int const blk = t / tiles_per_block, x = t - blk * tiles_per_block;
+    if (t < ntiles && 8 * x + c < n2) cols_v3_request<FMT, N2C>(raw, in + (long)blk * a.hop + 8 * x + c + (long)ul * n2, n2);
+  }
+  mbar_wait(&tbar, 0);
+  for (; t < ntiles; t += G) {
+    int const blk = t / tiles_per_block, x = t - blk * tiles_per_block;
+    int const mblk = a.mid_mod ? blk % a.mid_mod : blk;
+    int const n2g = 8 * x + c;
+    bool const col_ok = n2g < n2;
+    // ---- stage 0 on the words requested one tile ago -------------------------------------------
+    unsigned long long energy = 0;
+    unsigned int clips = 0;
+    if (col_ok) {
+#pragma unroll
+      for (int it = 0; it < 3; it++) {
+        int const j = ul + UPI * it;
+        float2 xv[R0];
+#pragma unroll
+        for (int m = 0; m < R0; m++) {
+          short lo = (short)(raw[it][m] & 0xffff), hi = (short)((unsigned)raw[it][m] >> 16);
+          if (FMT == 2) {
+            if (a.derandomize) {  // lsb set -> flip bits 1..15 (rx888.c:707-712)
+              lo ^= (short)((lo & 1) ? 0xfffe : 0);
+              hi ^= (short)((hi & 1) ? 0xfffe : 0);
+            }
+            if (a.stats && (long)(j + S0 * m) * n2 + n2g >= a.first_new) {
+              energy += (unsigned long long)((int)lo * lo) + (unsigned long long)((int)hi * hi);
+              clips += (lo > 32766 || lo < -32766) + (hi > 32766 || hi < -32766);
+            }
+          }
+          xv[m] = make_float2((float)lo, (float)hi);  // the int16 scale rides on the inter-pass twiddle
+        }
+        Dft<R0, false>::run(xv);
+        float2 *d = mycol + j;
+        d[0] = xv[0];
+#pragma unroll
+        for (int q = 1; q < R0; q++) d[q * S0] = cmul(xv[q], s_tw[(q - 1) * S0 + j]);  // twiddles straight from the table:
+                                                                                      // the look-ahead words own the registers
+      }
+    }
+    // ---- the next tile's words: in flight during stages 1 and 2 -----------------------------------
+    {
+      int const tn = t + G;
+      int const blkn = tn / tiles_per_block, xn = tn - blkn * tiles_per_block;
+      if (tn < ntiles && 8 * xn + c < n2) cols_v3_request<FMT, N2C>(raw, in + (long)blkn * a.hop + 8 * xn + c + (long)ul * n2, n2);
+    }
+    if (FMT == 2 && a.stats) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        energy += __shfl_xor_sync(0xffffffffu, energy, o);
+        clips += __shfl_xor_sync(0xffffffffu, clips, o);
+      }
+      if ((tid & 31) == 0 && (energy | clips)) {
+        atomicAdd(&a.stats[blk].energy, energy);
+        atomicAdd(&a.stats[blk].clips, clips);
+      }
+    }
+    __syncthreads();
+    // ---- stage 1 in shared memory: 12 blocks of 108, stride 9 -----------------------------------
+    if (col_ok) {
+#pragma unroll 1
+      for (int it = 0; it < 3; it++) {
+        float2 *p = mycol + (b0 + (UPI / S1) * it) * NSUB1 + j1;
+        float2 xv[R1];
+#pragma unroll
+        for (int m = 0; m < R1; m++) xv[m] = p[m * S1];
+        Dft<R1, false>::run(xv);
+        p[0] = xv[0];
+#pragma unroll
+        for (int q = 1; q < R1; q++) p[q * S1] = cmul(xv[q], tw1[(q - 1) * S1 + j1]);
+      }
+    }
+    // inter-pass factors of this tile: requested before the barrier, used after it
+    float2 twU[4];
+    if (col_ok) {
+#pragma unroll
+      for (int it = 0; it < 4; it++) twU[it] = __ldg(tb.twU + (long)n2g * 144 + ul + UPI * it);
+    }
+    if (tid < 72) s_twT[tid] = __ldg(tb.twT + (long)(8 * x) * 9 + tid);  // [8][9], table padded by 8 columns
+    __syncthreads();
+    // ---- stage 2 fused with the store: X[k1] * W_nc^{n2 k1} -> mid[k1][n2] ------------------------
+    if (col_ok) {
+      float2 *dst = a.mid + (long)mblk * nc + n2g + (long)kb0 * n2;
+      float const os = a.out_scale;
+#pragma unroll
+      for (int it = 0; it < 4; it++) {
+        int const u = ul + UPI * it;
+        float2 const *p = mycol + u * R2;
+        float2 xv[R2];
+#pragma unroll
+        for (int m = 0; m < R2; m++) xv[m] = p[m];
+        Dft<R2, false>::run(xv);
+        float2 const wb = make_float2(twU[it].x * os, twU[it].y * os);
+#pragma unroll
+        for (int q = 0; q < R2; q++) dst[(long)(3 * it + 144 * q) * n2] = cmul(xv[q], cmul(wb, s_twT[c * 9 + q]));
+      }
+    }
+    __syncthreads();  // the tile buffer is rewritten by the next stage 0
+  }
+}
 
 // ------------------------------------------------------------------ pass 2: rows, persistent ---
 template <bool REAL_SPLIT, int N1C = 0, bool HALVED = false>
