@@ -2,8 +2,9 @@
 //
 // Everything here works on a thread-private float2 x[R] that the compiler keeps in registers
 // (all indices are literals after unrolling).  Primitive radices 2,3,4,5,7 are written out;
-// every other radix is a two-level Cooley-Tukey split R = R1*R2 with compile-time twiddles
-// from wconst.cuh.  INV selects exp(+i..) (the reference's FFTW_BACKWARD, filter.c:359).
+// a radix with two coprime factors (6, 10, 12, 15, 20, 24, 36 ...) is a Good-Thomas prime-factor
+// split R = R1*R2 -- index maps only, no twiddles between the two levels -- and a prime power
+// (8, 9, 16, 25 ...) a two-level Cooley-Tukey split with compile-time twiddles from wconst.cuh.  INV selects exp(+i..) (the reference's FFTW_BACKWARD, filter.c:359).
 #pragma once
 #include <cuda_runtime.h>
 #include "wconst.cuh"
@@ -124,30 +125,74 @@ template <int R, bool INV> __device__ __forceinline__ float2 mul_root(float2 a, 
   return INV ? cmulc(a, w) : cmul(a, w);
 }
 
+// R1 of the prime-factor split: the full power of the smallest prime in r (== r for a prime power)
+constexpr int prime_power_first(int r) {
+  int const p = (r % 2 == 0) ? 2 : (r % 3 == 0) ? 3 : (r % 5 == 0) ? 5 : (r % 7 == 0) ? 7 : 1;
+  if (p == 1) return 1;
+  int q = 1;
+  while (r % p == 0) {
+    q *= p;
+    r /= p;
+  }
+  return q;
+}
+constexpr int inv_mod(int a, int m) {  // a^-1 mod m, gcd(a, m) = 1, m > 1
+  for (int i = 1; i < m; i++)
+    if ((a * i) % m == 1) return i;
+  return 0;
+}
+
 template <int R, bool INV> struct Dft {
-  static constexpr int R1 = split_first(R);
+  static constexpr int Q = prime_power_first(R);
+  static constexpr bool PFA = (Q != R);  // two coprime factors
+  static constexpr int R1 = PFA ? Q : split_first(R);
   static constexpr int R2 = R / R1;
   static_assert(R1 > 1, "radix has an unsupported prime factor");
-  // x natural order in, natural order out.  n = n1*R2 + n2 ; k = k1 + R1*k2
+  // x natural order in, natural order out
   static __device__ __forceinline__ void run(float2 (&x)[R]) {
     float2 y[R];
+    if constexpr (PFA) {
+      // Good-Thomas: n = (R2 n1 + R1 n2) mod R,  k = (R2 (R2^-1 mod R1) k1 + R1 (R1^-1 mod R2) k2) mod R
+      //   => W_R^{nk} = W_R1^{n1 k1} W_R2^{n2 k2}: R2 DFTs of length R1, then R1 of length R2, nothing between
+      constexpr int A = R2 * inv_mod(R2 % R1, R1), B = R1 * inv_mod(R1 % R2, R2);
 #pragma unroll
-    for (int n2 = 0; n2 < R2; n2++) {
-      float2 a[R1];
+      for (int n2 = 0; n2 < R2; n2++) {
+        float2 a[R1];
 #pragma unroll
-      for (int n1 = 0; n1 < R1; n1++) a[n1] = x[n1 * R2 + n2];
-      Dft<R1, INV>::run(a);
+        for (int n1 = 0; n1 < R1; n1++) a[n1] = x[(R2 * n1 + R1 * n2) % R];
+        Dft<R1, INV>::run(a);
 #pragma unroll
-      for (int k1 = 0; k1 < R1; k1++) y[k1 * R2 + n2] = mul_root<R, INV>(a[k1], n2 * k1);
-    }
+        for (int k1 = 0; k1 < R1; k1++) y[k1 * R2 + n2] = a[k1];
+      }
 #pragma unroll
-    for (int k1 = 0; k1 < R1; k1++) {
-      float2 b[R2];
+      for (int k1 = 0; k1 < R1; k1++) {
+        float2 b[R2];
 #pragma unroll
-      for (int n2 = 0; n2 < R2; n2++) b[n2] = y[k1 * R2 + n2];
-      Dft<R2, INV>::run(b);
+        for (int n2 = 0; n2 < R2; n2++) b[n2] = y[k1 * R2 + n2];
+        Dft<R2, INV>::run(b);
 #pragma unroll
-      for (int k2 = 0; k2 < R2; k2++) x[k1 + R1 * k2] = b[k2];
+        for (int k2 = 0; k2 < R2; k2++) x[(A * k1 + B * k2) % R] = b[k2];
+      }
+    } else {
+      // Cooley-Tukey: n = n1*R2 + n2 ; k = k1 + R1*k2
+#pragma unroll
+      for (int n2 = 0; n2 < R2; n2++) {
+        float2 a[R1];
+#pragma unroll
+        for (int n1 = 0; n1 < R1; n1++) a[n1] = x[n1 * R2 + n2];
+        Dft<R1, INV>::run(a);
+#pragma unroll
+        for (int k1 = 0; k1 < R1; k1++) y[k1 * R2 + n2] = mul_root<R, INV>(a[k1], n2 * k1);
+      }
+#pragma unroll
+      for (int k1 = 0; k1 < R1; k1++) {
+        float2 b[R2];
+#pragma unroll
+        for (int n2 = 0; n2 < R2; n2++) b[n2] = y[k1 * R2 + n2];
+        Dft<R2, INV>::run(b);
+#pragma unroll
+        for (int k2 = 0; k2 < R2; k2++) x[k1 + R1 * k2] = b[k2];
+      }
     }
   }
 };

@@ -362,6 +362,8 @@ struct kgpu_master {
   int static_cols = 0, static_rows = 0;  // which specialised kernels apply (0 = generic)
   float2 *d_mid = nullptr;
   int mid_blocks = 0;
+  alignas(64) CUtensorMap mid_map;  // 5-D view (n2, t2, t1, t0, block) of d_mid for the TMA tile store of fwd_cols_v2<.., TMAST>
+  bool mid_map_ok = false;
   size_t smem1 = 0, smem2 = 0;
   // notches
   NotchDev *d_notch = nullptr;
@@ -493,8 +495,10 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
         set_smem((const void *)fwd_cols_v2<2>, sv1) || set_smem((const void *)fwd_rows_v2<true>, sv2) ||
         set_smem((const void *)fwd_rows_v2<false>, sv2) ||
         set_smem((const void *)fwd_cols_v2<0, 1250>, sv1) || set_smem((const void *)fwd_cols_v2<1, 1250>, sv1) ||
-        set_smem((const void *)fwd_cols_v2<2, 1250>, sv1) || set_smem((const void *)fwd_cols_v2<1, 1250, 1>, sv1) ||
-        set_smem((const void *)fwd_rows_v2<true, 1296, true>, sv2) ||
+        set_smem((const void *)fwd_cols_v2<2, 1250>, sv1) || set_smem((const void *)fwd_cols_v2<1, 1250, 1>, sv1) || set_smem((const void *)fwd_cols_v2<1, 1250, 2>, sv1) ||
+        set_smem((const void *)fwd_rows_v2<true, 1296, true>, sv2) || set_smem((const void *)fwd_rows_v2<true, 1296, true, true>, sv2) ||
+        set_smem((const void *)fwd_cols_v2<0, 1250, 0, true>, sv1 + 128) || set_smem((const void *)fwd_cols_v2<1, 1250, 0, true>, sv1 + 128) ||
+        set_smem((const void *)fwd_cols_v2<2, 1250, 0, true>, sv1 + 128) ||
         set_smem((const void *)fwd_cols_v3<1, 1250>, sv1) || set_smem((const void *)fwd_cols_v3<2, 1250>, sv1) ||
         set_smem((const void *)fwd_rows_v3<true, 1296, true>, sv3) || set_smem((const void *)fwd_rows_v3<false, 1296, false>, sv3) ||
         set_smem((const void *)fwd_rows_v3<true, 0, false>, sv3) || set_smem((const void *)fwd_rows_v3<false, 0, false>, sv3) || set_smem((const void *)fwd_rows_v2<false, 1296, false>, sv2) ||
@@ -555,6 +559,32 @@ extern "C" int kgpu_master_describe(kgpu_master const *m, char *buf, int buflen)
   return 0;
 }
 
+// 5-D tensor map of the inter-pass buffer for the column pass's tile store: coordinates
+// (n2, t2, t1, t0, block) with k1 = t0 + 12 t1 + 144 t2, box = one 8-column tile.  The encoder lives in
+// the driver (libcuda); it is looked up at run time so that the library links against cudart only.
+static bool encode_mid_map(kgpu_master *m) {
+  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) {
+      cudaGetLastError();
+      return false;
+    }
+    fn = (encode_fn)p;
+  }
+  cuuint64_t const n2 = (cuuint64_t)m->sp.n2;
+  cuuint64_t dims[5] = {n2, 9, 12, 12, (cuuint64_t)m->mid_blocks};
+  cuuint64_t strides[4] = {144 * n2 * 8, 12 * n2 * 8, n2 * 8, (cuuint64_t)m->nc * 8};
+  cuuint32_t box[5] = {8, 9, 12, 3, 1}, estr[5] = {1, 1, 1, 1, 1};
+  CUresult const r = fn(&m->mid_map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, m->d_mid, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float scale, int derandomize, int nblocks,
                             void *d_spec, void *d_stats, void *stream) {
   if (!m || !d_in || !d_spec || nblocks < 1) return fail("kgpu_forward: bad arguments");
@@ -566,6 +596,7 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
     m->mid_blocks = 0;
     CUDA_OK(cudaMalloc(&m->d_mid, sizeof(float2) * (size_t)m->nc * (size_t)nblocks));
     m->mid_blocks = nblocks;
+    m->mid_map_ok = (m->static_cols == 1296) && encode_mid_map(m);
   }
   Pass1Args a1;
   a1.in = d_in;
@@ -610,20 +641,25 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
       // folded into the inter-pass twiddle
       halved = (m->in_type == KGPU_REAL) && m->static_rows == 1250;
       a1.out_scale = (fmt == KGPU_FMT_I16 ? scale : 1.0f) * (halved ? 0.5f : 1.0f);
-      if (m->sp.n2 == 1250 && f != 0 && g_tuning[9].load() == 1) {  // persistent, next tile's words in flight
+      if (m->sp.n2 == 1250 && m->mid_map_ok && g_tuning[11].load() == 1) {  // TMA tile store
+        if (f == 0) fwd_cols_v2<0, 1250, 0, true><<<g1, 288, sv1 + 128, st>>>(a1, t2, m->mid_map);
+        else if (f == 1) fwd_cols_v2<1, 1250, 0, true><<<g1, 288, sv1 + 128, st>>>(a1, t2, m->mid_map);
+        else fwd_cols_v2<2, 1250, 0, true><<<g1, 288, sv1 + 128, st>>>(a1, t2, m->mid_map);
+      } else if (m->sp.n2 == 1250 && f != 0 && g_tuning[9].load() == 1) {  // persistent, next tile's words in flight
         int const tpb = (int)g1.x, ntiles = tpb * nblocks;
         int const grid = std::min(2 * sm_count(), ntiles);
         if (f == 1) fwd_cols_v3<1, 1250><<<grid, 288, sv1, st>>>(a1, t2, tpb, ntiles);
         else fwd_cols_v3<2, 1250><<<grid, 288, sv1, st>>>(a1, t2, tpb, ntiles);
       } else if (m->sp.n2 == 1250) {
-        if (f == 0) fwd_cols_v2<0, 1250><<<g1, 288, sv1, st>>>(a1, t2);
-        else if (f == 1 && g_tuning[2].load() == 1) fwd_cols_v2<1, 1250, 1><<<g1, 288, sv1, st>>>(a1, t2);
-        else if (f == 1) fwd_cols_v2<1, 1250><<<g1, 288, sv1, st>>>(a1, t2);
-        else fwd_cols_v2<2, 1250><<<g1, 288, sv1, st>>>(a1, t2);
+        if (f == 0) fwd_cols_v2<0, 1250><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
+        else if (f == 1 && g_tuning[2].load() == 1) fwd_cols_v2<1, 1250, 1><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
+        else if (f == 1 && g_tuning[2].load() == 2) fwd_cols_v2<1, 1250, 2><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
+        else if (f == 1) fwd_cols_v2<1, 1250><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
+        else fwd_cols_v2<2, 1250><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
       } else {
-        if (f == 0) fwd_cols_v2<0><<<g1, 288, sv1, st>>>(a1, t2);
-        else if (f == 1) fwd_cols_v2<1><<<g1, 288, sv1, st>>>(a1, t2);
-        else fwd_cols_v2<2><<<g1, 288, sv1, st>>>(a1, t2);
+        if (f == 0) fwd_cols_v2<0><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
+        else if (f == 1) fwd_cols_v2<1><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
+        else fwd_cols_v2<2><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
       }
     } else if (use_static && m->static_cols == 12960 && fmt == KGPU_FMT_I16) {
       size_t const s1 = sizeof(float2) * ((size_t)8 * static_pitch(phys_len<S1296b>()) + static_tw_count<S1296b>() + 2 + 8 * 42);
@@ -681,7 +717,8 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
         else if (a2.real_split) fwd_rows_v3<true, 0, false><<<grid, 512, sv3, st>>>(a2, tb, m->n_item_ctas, ntiles);
         else if (m->sp.n1 == 1296) fwd_rows_v3<false, 1296, false><<<grid, 512, sv3, st>>>(a2, tb, m->n_item_ctas, ntiles);
         else fwd_rows_v3<false, 0, false><<<grid, 512, sv3, st>>>(a2, tb, m->n_item_ctas, ntiles);
-      } else if (a2.real_split && halved) fwd_rows_v2<true, 1296, true><<<g2, 256, sv2, st>>>(a2, tb);
+      } else if (a2.real_split && halved && g_tuning[10].load() == 1) fwd_rows_v2<true, 1296, true, true><<<g2, 256, sv2, st>>>(a2, tb);
+      else if (a2.real_split && halved) fwd_rows_v2<true, 1296, true><<<g2, 256, sv2, st>>>(a2, tb);
       else if (a2.real_split) fwd_rows_v2<true><<<g2, 256, sv2, st>>>(a2, tb);
       else if (m->sp.n1 == 1296) fwd_rows_v2<false, 1296, false><<<g2, 256, sv2, st>>>(a2, tb);
       else fwd_rows_v2<false><<<g2, 256, sv2, st>>>(a2, tb);

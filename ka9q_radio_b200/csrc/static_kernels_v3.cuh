@@ -18,7 +18,7 @@ namespace kfft {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { fence_proxy_async_smem(); }
 
 
 // ------------------------------------------------------------------ pass 1: columns, persistent --
