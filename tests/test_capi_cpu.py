@@ -76,3 +76,21 @@ def test_no_oracle_in_product():
     for p in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.c")) + list(pkg.rglob("Makefile")):
         txt = p.read_text()
         assert "oracle" not in txt.replace("no oracle", ""), p
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """`bench.py --impl reference` (the driver's reference arm) times oracle/_ref (or the port) on the
+    host cores and prints the contract's JSON line; no GPU involved."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    out = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--ref-blocks", "2"], capture_output=True, text=True, timeout=600, check=True)
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Msamples/s" and line["value"] > 0
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and "sample" in cb
