@@ -353,6 +353,45 @@ def test_cfg2_full_size_channels_subset(oracle, cuda_dev):
     assert worst < TOL, worst
 
 
+def test_cfg2_full_size_all_channels_tone_comb(cuda_dev):
+    """Size-independent property at BASELINE.json's full cfg-2 size, ALL 1024 channels in one batched launch of
+    4 blocks: a real tone A*cos at an exact bin centre whose index is a multiple of the overlap factor (V = 5)
+    comes out of its channel as a CONSTANT complex sample of magnitude A/sqrt(2) from block 1 on
+    (filter.c:1020-1025 gain normalisation, radio.c:1491-1497 block phase) -- checked for every channel, each
+    with its own amplitude, and against leakage from the 1023 other tones.  No oracle needed at this size."""
+    from ka9q_radio_b200 import capi
+
+    L, M, nb, nch = 2592000, 648001, 4, 1024
+    N = L + M - 1
+    bins = [5 * (3000 + 150 * k) for k in range(nch)]          # 750-bin (30 kHz) raster, all multiples of V = 5
+    amps = np.array([60.0 + 18.0 * (k % 11) for k in range(nch)])  # int16 units: rounding noise ~1e-4 of A in a channel
+    rng = np.random.default_rng(5)
+    ph = rng.uniform(0, 2 * np.pi, nch)
+    spec = np.zeros(N // 2 + 1, np.complex128)
+    spec[bins] = 0.5 * N * amps * np.exp(1j * ph)                # irfft -> sum A cos(2 pi b n / N + ph), period N
+    period = np.fft.irfft(spec, N)
+    reps = -(-(nb * L) // N)
+    xi = np.rint(np.tile(period, reps)[: nb * L]).astype(np.int16)
+    assert np.abs(xi).max() < 32000
+    cz = _mk(L, M, capi.KGPU_REAL, cuda_dev, cap=nch)
+    for b in bins:
+        cz.add_channel(480, b, -8000 / 24000, 8000 / 24000, 11.0)
+    spc, out = cz.alloc_spectra(nb), cz.alloc_outputs(nb)
+    cz.forward(cz.stage_stream(xi), nb, spc, scale=1.0)
+    cz.channels(spc, nb, out)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().reshape(nb, -1)[:, : nch * 480].reshape(nb, nch, 480)
+    cz.close()
+    want = amps / np.sqrt(2.0)
+    steady = got[1:]                                             # block 0 still contains the zero history
+    mag = np.abs(steady)
+    assert np.abs(mag - want[None, :, None]).max() / want.min() < 3e-3
+    const = np.abs(steady - steady[:, :, :1]).max(axis=(0, 2)) / want        # constant within a block
+    assert const.max() < 3e-3
+    # the same complex value in every block (tone bin divisible by V: no block-to-block phase step)
+    assert (np.abs(steady[1:, :, 0] - steady[:1, :, 0]) / want).max() < 3e-3
+
+
 def test_cfg3_mixed_rates_full_size(oracle, cuda_dev):
     """cfg-3: RX888 input, SSB channels at 12/24/48 kHz (preset usb: +50..+3000 Hz, beta 11) in one bank."""
     from ka9q_radio_b200 import capi
