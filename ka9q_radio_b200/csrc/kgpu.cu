@@ -362,7 +362,7 @@ struct kgpu_master {
   int static_cols = 0, static_rows = 0;  // which specialised kernels apply (0 = generic)
   float2 *d_mid = nullptr;
   int mid_blocks = 0;
-  alignas(64) CUtensorMap mid_map;  // 5-D view (n2, t2, t1, t0, block) of d_mid for the TMA tile store of fwd_cols_v2<.., TMAST>
+  alignas(64) CUtensorMap mid_map{};  // 5-D view (n2, t2, t1, t0, block) of d_mid for the TMA tile store of fwd_cols_v2<.., TMAST>
   bool mid_map_ok = false;
   size_t smem1 = 0, smem2 = 0;
   // notches
