@@ -362,6 +362,8 @@ struct kgpu_master {
   int static_cols = 0, static_rows = 0;  // which specialised kernels apply (0 = generic)
   float2 *d_mid = nullptr;
   int mid_blocks = 0;
+  cudaStream_t aux[2] = {nullptr, nullptr};   // internal streams of the sub-batched forward (tuning 12)
+  cudaEvent_t aux_done[2] = {nullptr, nullptr}, aux_start = nullptr;
   alignas(64) CUtensorMap mid_map{};  // 5-D view (n2, t2, t1, t0, block) of d_mid for the TMA tile store of fwd_cols_v2<.., TMAST>
   bool mid_map_ok = false;
   size_t smem1 = 0, smem2 = 0;
@@ -536,6 +538,11 @@ extern "C" void kgpu_master_destroy(kgpu_master *m) {
   cudaFree(m->d_twT);
   cudaFree(m->d_mid);
   cudaFree(m->d_notch);
+  for (int i = 0; i < 2; i++) {
+    if (m->aux[i]) cudaStreamDestroy(m->aux[i]);
+    if (m->aux_done[i]) cudaEventDestroy(m->aux_done[i]);
+  }
+  if (m->aux_start) cudaEventDestroy(m->aux_start);
   delete m;
 }
 extern "C" int kgpu_master_points(kgpu_master const *m) { return m ? m->N : -1; }
@@ -585,19 +592,9 @@ static bool encode_mid_map(kgpu_master *m) {
   return r == CUDA_SUCCESS;
 }
 
-extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float scale, int derandomize, int nblocks,
-                            void *d_spec, void *d_stats, void *stream) {
-  if (!m || !d_in || !d_spec || nblocks < 1) return fail("kgpu_forward: bad arguments");
-  cudaStream_t st = (cudaStream_t)stream;
-  if (m->mid_blocks < nblocks) {
-    CUDA_OK(cudaStreamSynchronize(st));
-    cudaFree(m->d_mid);
-    m->d_mid = nullptr;
-    m->mid_blocks = 0;
-    CUDA_OK(cudaMalloc(&m->d_mid, sizeof(float2) * (size_t)m->nc * (size_t)nblocks));
-    m->mid_blocks = nblocks;
-    m->mid_map_ok = (m->static_cols == 1296) && encode_mid_map(m);
-  }
+// One launch pair (column pass, row pass) over `nblocks` consecutive blocks on stream `st`, inter-pass data in `mid`.
+static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, int derandomize, int nblocks, void *d_spec,
+                        void *d_stats, cudaStream_t st, float2 *mid) {
   Pass1Args a1;
   a1.in = d_in;
   a1.hop = (m->in_type == KGPU_REAL) ? m->L / 2 : m->L;
@@ -609,12 +606,11 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
   a1.scale = scale;
   a1.derandomize = derandomize;
   a1.first_new = (m->in_type == KGPU_REAL) ? (m->M - 1) / 2 : (m->M - 1);
-  a1.mid = m->d_mid;
+  a1.mid = mid;
   a1.stats = (fmt == KGPU_FMT_I16) ? (IngestStats *)d_stats : nullptr;
   a1.dbg = (unsigned long long *)g_dbg_buf;
   a1.mid_mod = g_tuning[7].load();
   a1.pf_dist = g_tuning[3].load() >= 2 ? g_tuning[3].load() - 1 : 0;
-  if (a1.stats) CUDA_OK(cudaMemsetAsync(d_stats, 0, sizeof(IngestStats) * (size_t)nblocks, st));
   dim3 const g1((unsigned)((m->sp.n2 + kTile - 1) / kTile), (unsigned)nblocks);
   if (g_tuning[3].load() == 1) {  // experiment: pull the input windows into L2 with coalesced requests first
     long const esz = (m->in_type == KGPU_REAL) ? (fmt == KGPU_FMT_I16 ? 2 : 4) : (fmt == KGPU_FMT_I16 ? 4 : 8);
@@ -691,7 +687,7 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
   }
   g_launches++;
   Pass2Args a2;
-  a2.mid = m->d_mid;
+  a2.mid = mid;
   a2.n1 = m->sp.n1;
   a2.n2 = m->sp.n2;
   a2.nc = m->nc;
@@ -738,6 +734,52 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
   }
   g_launches++;
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float scale, int derandomize, int nblocks,
+                            void *d_spec, void *d_stats, void *stream) {
+  if (!m || !d_in || !d_spec || nblocks < 1) return fail("kgpu_forward: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m->mid_blocks < nblocks) {
+    CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(m->d_mid);
+    m->d_mid = nullptr;
+    m->mid_blocks = 0;
+    CUDA_OK(cudaMalloc(&m->d_mid, sizeof(float2) * (size_t)m->nc * (size_t)nblocks));
+    m->mid_blocks = nblocks;
+    m->mid_map_ok = (m->static_cols == 1296) && encode_mid_map(m);
+  }
+  if (fmt == KGPU_FMT_I16 && d_stats) CUDA_OK(cudaMemsetAsync(d_stats, 0, sizeof(IngestStats) * (size_t)nblocks, st));
+  int const sub = g_tuning[12].load();
+  if (sub <= 0 || 2 * sub > nblocks) return forward_span(m, d_in, fmt, scale, derandomize, nblocks, d_spec, d_stats, st, m->d_mid);
+  // Experiment (tuning 12 = S): sub-batches of S blocks alternate between two internal streams, each with its own
+  // S-block half of the inter-pass buffer, so that `mid` (13 MB per block) is re-read from L2 instead of DRAM and
+  // the tail of one launch overlaps the head of the next.
+  if (!m->aux[0]) {
+    for (int i = 0; i < 2; i++) {
+      CUDA_OK(cudaStreamCreateWithFlags(&m->aux[i], cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&m->aux_done[i], cudaEventDisableTiming));
+    }
+    CUDA_OK(cudaEventCreateWithFlags(&m->aux_start, cudaEventDisableTiming));
+  }
+  CUDA_OK(cudaEventRecord(m->aux_start, st));
+  CUDA_OK(cudaStreamWaitEvent(m->aux[0], m->aux_start, 0));
+  CUDA_OK(cudaStreamWaitEvent(m->aux[1], m->aux_start, 0));
+  size_t const in_bytes_per_block =
+      (size_t)m->L * ((m->in_type == KGPU_REAL) ? (fmt == KGPU_FMT_I16 ? 2 : 4) : (fmt == KGPU_FMT_I16 ? 4 : 8));
+  for (int s = 0, b0 = 0; b0 < nblocks; s++, b0 += sub) {
+    int const nb = std::min(sub, nblocks - b0);
+    int const rc = forward_span(m, (char const *)d_in + (size_t)b0 * in_bytes_per_block, fmt, scale, derandomize, nb,
+                                (float2 *)d_spec + (size_t)b0 * (size_t)m->spec_stride,
+                                d_stats ? (void *)((IngestStats *)d_stats + b0) : nullptr, m->aux[s & 1],
+                                m->d_mid + (size_t)(s & 1) * (size_t)sub * (size_t)m->nc);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < 2; i++) {
+    CUDA_OK(cudaEventRecord(m->aux_done[i], m->aux[i]));
+    CUDA_OK(cudaStreamWaitEvent(st, m->aux_done[i], 0));
+  }
   return 0;
 }
 
