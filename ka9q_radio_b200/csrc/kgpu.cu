@@ -1151,6 +1151,19 @@ template <class P> static int launch_chan_v2(ChanArgs const &a, int n, int nbloc
   return 0;
 }
 
+template <class P> static int launch_chan_v3(ChanArgs const &a, int n, int nblocks, cudaStream_t st) {
+  constexpr int R0 = P::rad(0), S0 = P::len / R0, TPC = 128 / (S0 > R0 ? S0 : R0);
+  size_t const sm = sizeof(float2) * ((size_t)(2 * P::len + 6) * TPC + static_tw_count<P>() + 2);
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (set_smem((const void *)chan_v3<P>, sm)) return -1;
+    attr_done = true;
+  }
+  dim3 const g((unsigned)((n + TPC - 1) / TPC), (unsigned)nblocks);
+  chan_v3<P><<<g, 128, sm, st>>>(a);
+  return 0;
+}
+
 template <class P> static int launch_chan_static(ChanArgs const &a, int n, int nblocks, cudaStream_t st) {
   size_t const sm = sizeof(float2) * ((size_t)(2 * P::len + 4) * kChanWarps + static_tw_count<P>() + 2);
   static bool attr_done = false;
@@ -1183,6 +1196,11 @@ static int launch_chan(kgpu_bank *b, const void *d_spec, int nblocks, void *d_ou
   g_launches++;
   TilePlan const *tp = host_tile_plan(plan);
   if (g_static_on.load()) {
+    if (g_tuning[6].load() == 2 && !a.wrap) {  // lane-packed variant: REAL master, no ISB channel in the bank
+      bool isb = false;
+      for (int i = 0; i < b->nchan && !isb; i++) isb = b->ch[(size_t)i].defined && (b->ch[(size_t)i].flags & 1);
+      if (!isb && plan_is<S600>(tp)) return launch_chan_v3<S600>(a, n, nblocks, st);
+    }
     if (g_tuning[6].load() != 1) {
       if (plan_is<S600>(tp)) return launch_chan_v2<S600>(a, n, nblocks, st);
       if (plan_is<S300>(tp)) return launch_chan_v2<S300>(a, n, nblocks, st);

@@ -390,3 +390,127 @@ __global__ void __launch_bounds__(512, 1) fwd_rows_v3(Pass2Args const a, FwdTabl
 }
 
 }  // namespace kfft
+
+namespace kfft {
+
+// ------------------------------------------------------------------ channels, lane-packed --------
+// chan_v2 gives one warp to a (channel, block) task and keeps only S0 = 25 of its lanes busy in stage 0 and
+// R0 = 24 in stage 1 (600 = 24 * 25); ncu shows the kernel issue-bound (69 %).  Here a 4-warp CTA takes
+// TPC = 128 / S0 tasks (5 for the 600-point plan): thread t works for task t / S0 as lane t % S0 in stage 0
+// and for task t / R0 as lane t % R0 in stage 1, so 125 / 120 of the 128 lanes carry butterflies.  Tasks no
+// longer coincide with warps, hence block barriers instead of __syncwarp.  REAL masters without ISB channels
+// only (the launcher falls back to chan_v2 otherwise).
+template <class P>
+__global__ void __launch_bounds__(128) chan_v3(ChanArgs const a) {
+  static_assert(P::nst == 2, "two-stage plans only");
+  constexpr int NS = P::len, TOP = (NS + 1) / 2, R0 = P::rad(0), R1 = P::rad(1), S0 = NS / R0;
+  static_assert(S0 == R1 && NS % 2 == 0, "plan shape");
+  constexpr int TPC = 128 / (S0 > R0 ? S0 : R0);  // tasks per CTA
+  constexpr int XS = NS + 4, TP = NS + XS + 2;      // per-task pitch: even (16-byte TMA alignment)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bars[TPC];
+  __shared__ __align__(8) uint64_t tbar;
+  float2 *base = reinterpret_cast<float2 *>(smem_raw);
+  float2 *s_tw = base + TPC * TP;
+  int const tid = threadIdx.x, blk = blockIdx.y;
+  int const first_task = blockIdx.x * TPC;
+  float2 const *X = a.spec + (long)blk * a.spec_stride;
+
+  auto load_desc = [&](int tk, ChanDesc &d) -> bool {  // false: no such task / disabled channel
+    int const oi = first_task + tk;
+    d.plan = -1;
+    if (tk >= TPC || oi >= a.norder) return false;
+    d = a.desc[a.order ? a.order[oi] : a.chan_base + oi];
+    return d.plan >= 0;
+  };
+
+  // ---- fetch: thread tk < TPC issues the two bulk copies of task tk --------------------------------------
+  if (tid == 0) {
+    mbar_init(&tbar, 1);
+    for (int i = 0; i < TPC; i++) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+    constexpr uint32_t TWB = (uint32_t)((static_tw_count<P>() + 1) & ~1) * 8u;
+    int p0 = -1;
+    for (int i = 0; i < TPC && p0 < 0; i++) {
+      ChanDesc d;
+      if (load_desc(i, d)) p0 = d.plan;
+    }
+    if (p0 >= 0) {
+      mbar_expect_tx(&tbar, TWB);
+      bulk_g2s(s_tw, c_plans[p0].tw, TWB, &tbar);
+    } else
+      mbar_arrive(&tbar);
+  }
+  __syncthreads();
+  if (tid < TPC) {
+    ChanDesc d;
+    if (load_desc(tid, d) && d.ncopy > 0) {
+      int const qlo = d.dir > 0 ? d.q0 : d.q0 - (d.ncopy - 1);
+      int const qa = qlo & ~1, qhi = qlo + d.ncopy - 1;
+      uint32_t const nx = (uint32_t)(((qhi - qa + 1) + 1) & ~1);
+      float2 *col = base + tid * TP, *xs = col + NS;
+      mbar_expect_tx(&bars[tid], nx * 8 + NS * 8);
+      bulk_g2s(xs, X + qa, nx * 8, &bars[tid]);
+      bulk_g2s(col, a.resp + d.resp_off, NS * 8, &bars[tid]);
+    } else
+      mbar_arrive(&bars[tid]);
+  }
+  mbar_wait(&tbar, 0);
+
+  // ---- stage 0 with the slice x response product formed on the fly ------------------------------------------
+  {
+    int const tk = tid / S0, lane = tid - tk * S0;
+    ChanDesc d;
+    if (load_desc(tk, d) && d.ncopy > 0) {
+      float2 *col = base + tk * TP;
+      float2 const *xs = col + NS;
+      int const qlo = d.dir > 0 ? d.q0 : d.q0 - (d.ncopy - 1);
+      int const qa = qlo & ~1;
+      mbar_wait(&bars[tk], 0);
+      float2 x[R0];
+#pragma unroll
+      for (int m = 0; m < R0; m++) {  // S[wp] = X[q(wp)] * R[wp], zero outside the master (filter.c:728-911)
+        int const wp = lane + S0 * m;
+        int t = wp - TOP;
+        if (t < 0) t += NS;
+        int const u = t - d.zlead;
+        bool const live = (u >= 0 && u < d.ncopy && wp != TOP);
+        float2 xv = xs[live ? (d.q0 + d.dir * u - qa) : 0];
+        if (d.dir < 0) xv.y = -xv.y;
+        float2 const v = cmul(xv, col[wp]);
+        x[m] = live ? v : make_float2(0.f, 0.f);
+      }
+      Dft<R0, true>::run(x);
+      // every response word of this task is consumed above by the lane that overwrites it below (wp = lane + S0 m)
+      col[lane] = x[0];
+#pragma unroll
+      for (int t = 1; t < R0; t++) col[lane + S0 * t] = cmulc(x[t], s_tw[(t - 1) * S0 + lane]);
+    }
+  }
+  __syncthreads();
+  // ---- stage 1 fused with the store: y[n], n = u + R0*t, keep n >= NS - olen --------------------------------
+  {
+    int const tk = tid / R0, lane = tid - tk * R0;
+    ChanDesc d;
+    if (load_desc(tk, d)) {
+      float2 *dst = a.out + (long)blk * a.out_stride + d.out_off;
+      if (d.ncopy <= 0) {
+        for (int i = lane; i < d.olen; i += R0) dst[i] = make_float2(0.f, 0.f);
+      } else {
+        float2 const *col = base + tk * TP;
+        float2 x[R1];
+#pragma unroll
+        for (int m = 0; m < R1; m++) x[m] = col[R1 * lane + m];
+        Dft<R1, true>::run(x);
+        int const first = NS - d.olen;
+#pragma unroll
+        for (int t = 0; t < R1; t++) {
+          int const n = lane + R0 * t;
+          if (n >= first) dst[n - first] = x[t];
+        }
+      }
+    }
+  }
+}
+
+}  // namespace kfft

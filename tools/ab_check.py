@@ -18,17 +18,25 @@ def setv(v):
 B = 5
 rng = np.random.default_rng(1)
 for name, in_type, L, M in (("real-i16", capi.KGPU_REAL, bench.L, bench.M), ("complex-f32", capi.KGPU_COMPLEX, bench.L // 2, (bench.M - 1) // 2 + 1)):
-    cz = Channelizer(L, M, in_type, dev, capacity=4)
+    cz = Channelizer(L, M, in_type, dev, capacity=64)
+    nch = 43
+    for k in range(nch):  # upright, inverted and band-edge channels (REAL: |shift| < N/2; COMPLEX: wraps)
+        sh = (750_000 + 9_973 * k) * (1 if k % 3 else -1) if in_type == capi.KGPU_REAL else (-800_000 + 37_001 * k)
+        cz.add_channel(480, sh, -1 / 3, 1 / 3, 11.0)
     if in_type == capi.KGPU_REAL:
         x = rng.integers(-3000, 3000, B * L, dtype=np.int16)
     else:
         x = (rng.standard_normal(B * L) + 1j * rng.standard_normal(B * L)).astype(np.complex64)
     d = cz.stage_stream(x)
-    ref = cz.alloc_spectra(B); setv("default"); cz.forward(d, B, ref, scale=bench.SCALE); torch.cuda.synchronize()
+    ref = cz.alloc_spectra(B); oref = cz.alloc_outputs(B); setv("default")
+    cz.forward(d, B, ref, scale=bench.SCALE); cz.channels(ref, B, oref); torch.cuda.synchronize()
     print(name, cz.master.describe())
     for v in sys.argv[1:]:
-        out = cz.alloc_spectra(B); out.zero_(); setv(v); cz.forward(d, B, out, scale=bench.SCALE); torch.cuda.synchronize()
+        out = cz.alloc_spectra(B); out.zero_(); oo = cz.alloc_outputs(B); oo.zero_(); setv(v)
+        cz.forward(d, B, out, scale=bench.SCALE); cz.channels(out, B, oo); torch.cuda.synchronize()
         nb = cz.master.bins
         diff = (out[:, :nb] - ref[:, :nb]).abs().max().item(); mag = ref[:, :nb].abs().max().item()
-        print("  variant %-10s max|diff| %.3e  rel %.3e  %s" % (v, diff, diff / mag, "OK" if diff / mag < 1e-6 else "MISMATCH"))
+        od = (oo - oref).abs().max().item(); om = oref.abs().max().item()
+        print("  variant %-10s spectrum max|diff| %.3e rel %.3e | channels max|diff| %.3e rel %.3e  %s"
+              % (v, diff, diff / mag, od, od / om, "OK" if diff / mag < 1e-6 and od / om < 1e-6 else "MISMATCH"))
     setv("default"); cz.close()
