@@ -8,99 +8,131 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "wconst.cuh"
+#ifndef KFFT_HD
+#define KFFT_HD __host__ __device__ __forceinline__
+#endif
 
 namespace kfft {
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+// ---- packed complex arithmetic ----------------------------------------------------------------
+// sm_100 has two-wide fp32 instructions (FADD2 / FMUL2 / FFMA2 on an aligned register pair) whose
+// operands take a half swap (.LO_HI), a per-half sign and a scalar broadcast for free.  A float2 IS
+// such a pair, so a complex add is ONE instruction and a complex multiply TWO (instead of 2 and 4):
+// the lane throughput of the FMA pipe is unchanged, but these kernels are bound by instruction
+// issue, not by the pipe (ncu: issue 45-69 %, FMA pipe 34-41 %).  On the host (tests) and with
+// KFFT_PACKED=0 the three primitives are plain scalar code with the same rounding (fmaf / mul / add).
+#ifndef KFFT_PACKED
+#define KFFT_PACKED 1
+#endif
+KFFT_HD float2 p_add(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && KFFT_PACKED
+  return __fadd2_rn(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
 }
-__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // a * conj(b)
-  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+KFFT_HD float2 p_mul(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && KFFT_PACKED
+  return __fmul2_rn(a, b);
+#else
+  return make_float2(a.x * b.x, a.y * b.y);
+#endif
 }
-__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+KFFT_HD float2 p_fma(float2 a, float2 b, float2 c) {  // a*b + c per half, one rounding each
+#if defined(__CUDA_ARCH__) && KFFT_PACKED
+  return __ffma2_rn(a, b, c);
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+KFFT_HD float2 bb(float s) { return make_float2(s, s); }  // scalar broadcast operand
+
+KFFT_HD float2 cadd(float2 a, float2 b) { return p_add(a, b); }
+KFFT_HD float2 csub(float2 a, float2 b) { return p_add(a, make_float2(-b.x, -b.y)); }
+KFFT_HD float2 cmul(float2 a, float2 b) {  // (ax bx - ay by, ay bx + ax by)
+  return p_fma(a, bb(b.x), p_mul(make_float2(-a.y, a.x), bb(b.y)));
+}
+KFFT_HD float2 cmulc(float2 a, float2 b) {  // a * conj(b) = (ax bx + ay by, ay bx - ax by)
+  return p_fma(a, bb(b.x), p_mul(make_float2(a.y, -a.x), bb(b.y)));
+}
+KFFT_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 // multiply by -i (forward quarter turn) or +i
-template <bool INV> __device__ __forceinline__ float2 rot90(float2 a) {
+template <bool INV> KFFT_HD float2 rot90(float2 a) {
   return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
 }
+// c + s * (-i or +i) * a  and  c - s * (-/+ i) * a : the quarter turn rides on the operand modifiers
+template <bool INV> KFFT_HD float2 fma_rot(float2 a, float s, float2 c) { return p_fma(rot90<INV>(a), bb(s), c); }
+template <bool INV> KFFT_HD float2 fms_rot(float2 a, float s, float2 c) { return p_fma(rot90<!INV>(a), bb(s), c); }
 
 template <int R, bool INV> struct Dft;
 
 template <bool INV> struct Dft<1, INV> {
-  static __device__ __forceinline__ void run(float2 (&)[1]) {}
+  static KFFT_HD void run(float2 (&)[1]) {}
 };
 template <bool INV> struct Dft<2, INV> {
-  static __device__ __forceinline__ void run(float2 (&x)[2]) {
+  static KFFT_HD void run(float2 (&x)[2]) {
     float2 const a = x[0], b = x[1];
     x[0] = cadd(a, b);
     x[1] = csub(a, b);
   }
 };
 template <bool INV> struct Dft<3, INV> {
-  static __device__ __forceinline__ void run(float2 (&x)[3]) {
+  static KFFT_HD void run(float2 (&x)[3]) {
     constexpr float S = 0.86602540378443864676f;
     float2 const a = x[0], t1 = cadd(x[1], x[2]), d = csub(x[1], x[2]);
-    float2 const t2 = make_float2(fmaf(-0.5f, t1.x, a.x), fmaf(-0.5f, t1.y, a.y));
-    // forward: X1 = t2 - i*S*d
-    float2 const r = rot90<INV>(make_float2(S * d.x, S * d.y));
+    float2 const t2 = p_fma(t1, bb(-0.5f), a);
+    // forward: X1 = t2 - i*S*d, X2 = t2 + i*S*d
     x[0] = cadd(a, t1);
-    x[1] = cadd(t2, r);
-    x[2] = csub(t2, r);
+    x[1] = fma_rot<INV>(d, S, t2);
+    x[2] = fms_rot<INV>(d, S, t2);
   }
 };
 template <bool INV> struct Dft<4, INV> {
-  static __device__ __forceinline__ void run(float2 (&x)[4]) {
+  static KFFT_HD void run(float2 (&x)[4]) {
     float2 const apc = cadd(x[0], x[2]), amc = csub(x[0], x[2]);
-    float2 const bpd = cadd(x[1], x[3]), bmd = rot90<INV>(csub(x[1], x[3]));
+    float2 const bpd = cadd(x[1], x[3]), bmd = csub(x[1], x[3]);
     x[0] = cadd(apc, bpd);
-    x[1] = cadd(amc, bmd);
+    x[1] = fma_rot<INV>(bmd, 1.0f, amc);
     x[2] = csub(apc, bpd);
-    x[3] = csub(amc, bmd);
+    x[3] = fms_rot<INV>(bmd, 1.0f, amc);
   }
 };
 template <bool INV> struct Dft<5, INV> {
-  static __device__ __forceinline__ void run(float2 (&x)[5]) {
+  static KFFT_HD void run(float2 (&x)[5]) {
     constexpr float C1 = 0.30901699437494742410f, C2 = -0.80901699437494742410f;
     constexpr float S1 = 0.95105651629515357212f, S2 = 0.58778525229247312917f;
     float2 const a = x[0];
     float2 const t1 = cadd(x[1], x[4]), t2 = cadd(x[2], x[3]);
     float2 const t3 = csub(x[1], x[4]), t4 = csub(x[2], x[3]);
-    float2 const u1 = make_float2(fmaf(C2, t2.x, fmaf(C1, t1.x, a.x)), fmaf(C2, t2.y, fmaf(C1, t1.y, a.y)));
-    float2 const u2 = make_float2(fmaf(C1, t2.x, fmaf(C2, t1.x, a.x)), fmaf(C1, t2.y, fmaf(C2, t1.y, a.y)));
-    float2 const v1 = rot90<INV>(make_float2(fmaf(S2, t4.x, S1 * t3.x), fmaf(S2, t4.y, S1 * t3.y)));
-    float2 const v2 = rot90<INV>(make_float2(fmaf(-S1, t4.x, S2 * t3.x), fmaf(-S1, t4.y, S2 * t3.y)));
+    float2 const u1 = p_fma(t2, bb(C2), p_fma(t1, bb(C1), a));
+    float2 const u2 = p_fma(t2, bb(C1), p_fma(t1, bb(C2), a));
+    float2 const w1 = p_fma(t4, bb(S2), p_mul(t3, bb(S1)));   // v1 = (-/+ i) w1
+    float2 const w2 = p_fma(t4, bb(-S1), p_mul(t3, bb(S2)));  // v2 = (-/+ i) w2
     x[0] = cadd(a, cadd(t1, t2));
-    x[1] = cadd(u1, v1);
-    x[2] = cadd(u2, v2);
-    x[3] = csub(u2, v2);
-    x[4] = csub(u1, v1);
+    x[1] = fma_rot<INV>(w1, 1.0f, u1);
+    x[2] = fma_rot<INV>(w2, 1.0f, u2);
+    x[3] = fms_rot<INV>(w2, 1.0f, u2);
+    x[4] = fms_rot<INV>(w1, 1.0f, u1);
   }
 };
 template <bool INV> struct Dft<7, INV> {
-  static __device__ __forceinline__ void run(float2 (&x)[7]) {
+  static KFFT_HD void run(float2 (&x)[7]) {
     constexpr float C1 = 0.62348980185873353053f, C2 = -0.22252093395631440429f, C3 = -0.90096886790241912624f;
     constexpr float S1 = 0.78183148246802980871f, S2 = 0.97492791218182360702f, S3 = 0.43388373911755812048f;
     float2 const a = x[0];
     float2 const p1 = cadd(x[1], x[6]), p2 = cadd(x[2], x[5]), p3 = cadd(x[3], x[4]);
     float2 const m1 = csub(x[1], x[6]), m2 = csub(x[2], x[5]), m3 = csub(x[3], x[4]);
-    auto comb = [&](float c1, float c2, float c3) {
-      return make_float2(fmaf(c3, p3.x, fmaf(c2, p2.x, fmaf(c1, p1.x, a.x))),
-                         fmaf(c3, p3.y, fmaf(c2, p2.y, fmaf(c1, p1.y, a.y))));
-    };
-    auto sinc = [&](float s1, float s2, float s3) {
-      return rot90<INV>(make_float2(fmaf(s3, m3.x, fmaf(s2, m2.x, s1 * m1.x)),
-                                    fmaf(s3, m3.y, fmaf(s2, m2.y, s1 * m1.y))));
-    };
+    auto comb = [&](float c1, float c2, float c3) { return p_fma(p3, bb(c3), p_fma(p2, bb(c2), p_fma(p1, bb(c1), a))); };
+    auto sinc = [&](float s1, float s2, float s3) { return p_fma(m3, bb(s3), p_fma(m2, bb(s2), p_mul(m1, bb(s1)))); };
     float2 const u1 = comb(C1, C2, C3), u2 = comb(C2, C3, C1), u3 = comb(C3, C1, C2);
-    float2 const v1 = sinc(S1, S2, S3), v2 = sinc(S2, -S3, -S1), v3 = sinc(S3, -S1, S2);
+    float2 const w1 = sinc(S1, S2, S3), w2 = sinc(S2, -S3, -S1), w3 = sinc(S3, -S1, S2);  // v = (-/+ i) w
     x[0] = cadd(a, cadd(p1, cadd(p2, p3)));
-    x[1] = cadd(u1, v1);
-    x[6] = csub(u1, v1);
-    x[2] = cadd(u2, v2);
-    x[5] = csub(u2, v2);
-    x[3] = cadd(u3, v3);
-    x[4] = csub(u3, v3);
+    x[1] = fma_rot<INV>(w1, 1.0f, u1);
+    x[6] = fms_rot<INV>(w1, 1.0f, u1);
+    x[2] = fma_rot<INV>(w2, 1.0f, u2);
+    x[5] = fms_rot<INV>(w2, 1.0f, u2);
+    x[3] = fma_rot<INV>(w3, 1.0f, u3);
+    x[4] = fms_rot<INV>(w3, 1.0f, u3);
   }
 };
 
@@ -115,7 +147,7 @@ constexpr int split_first(int r) {
 }
 
 // multiply by the compile-time root exp(-/+ 2*pi*i*e/R); trivial cases cost nothing or a swap
-template <int R, bool INV> __device__ __forceinline__ float2 mul_root(float2 a, int e) {
+template <int R, bool INV> KFFT_HD float2 mul_root(float2 a, int e) {
   e %= R;
   if (e == 0) return a;
   if (2 * e == R) return make_float2(-a.x, -a.y);
@@ -149,7 +181,7 @@ template <int R, bool INV> struct Dft {
   static constexpr int R2 = R / R1;
   static_assert(R1 > 1, "radix has an unsupported prime factor");
   // x natural order in, natural order out
-  static __device__ __forceinline__ void run(float2 (&x)[R]) {
+  static KFFT_HD void run(float2 (&x)[R]) {
     float2 y[R];
     if constexpr (PFA) {
       // Good-Thomas: n = (R2 n1 + R1 n2) mod R,  k = (R2 (R2^-1 mod R1) k1 + R1 (R1^-1 mod R2) k2) mod R

@@ -94,3 +94,21 @@ def test_bench_reference_arm_runs_on_cpu():
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     cb = line["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and "sample" in cb
+
+
+def test_butterfly_templates_on_host(tmp_path):
+    """fft_radix.cuh compiled for the HOST (the packed f32x2 primitives fall back to scalar code with the same
+    rounding): every radix the planner can pick, forward and inverse, against a float64 DFT."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(nvcc).exists():
+        pytest.skip("nvcc not available")
+    src = Path(__file__).resolve().parent / "host" / "dft_host_test.cu"
+    exe = tmp_path / "dft_host_test"
+    subprocess.run([nvcc, "-std=c++17", "-O1", "--expt-relaxed-constexpr", "-gencode", "arch=compute_100a,code=sm_100a",
+                    "-o", str(exe), str(src)], check=True, capture_output=True, timeout=600)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "all butterflies ok" in out.stdout, out.stdout[-2000:]
