@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(kChanWarps * 32) chan_static(ChanArgs const a)
 
   if (d.ncopy <= 0) {  // nothing of this channel overlaps the master spectrum: zeros (filter.c:823-832)
     for (int i = lane; i < d.olen; i += 32) dst[i] = make_float2(0.f, 0.f);
+    mbar_wait(&tbar, 0);  // never retire the CTA with its twiddle copy still in flight
     return;
   }
   int const qlo = d.dir > 0 ? d.q0 : d.q0 - (d.ncopy - 1);

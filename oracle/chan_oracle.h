@@ -73,6 +73,39 @@ void ko_siggen_tones_i16(int16_t *dst, long n, int ntones, double const *cycles_
 /* tuning (radio.c:1175-1199): shift = lrint(f/(fs/N)); returns -1 if |shift| >= N/2 */
 int ko_compute_tuning(int N, double samprate, double freq, int *shift, double *remainder);
 
+/* ---- oracle/chan_oracle_ext.c: the remaining slice variants and the per-channel steps after the filter ---- */
+/* beam synthesis, COMPLEX master -> COMPLEX slave (filter.c:756-775, weights :922-929) */
+void ko_slice_beam(int m_bins, float complex const *X, int s_bins, float complex const *R, int shift,
+                   double complex alpha, double complex beta, float complex *S);
+int ko_channel_block_beam(int m_bins, float complex const *X, int points, float complex const *R, int shift,
+                          double are, double aim, double bre, double bim, float complex *full);
+/* REAL output slaves (filter.c:794-809), c2r inverse (filter.c:386,914): S has points/2+1 bins, full has points reals */
+void ko_slice_realout(int in_type, int m_bins, float complex const *X, int points, float complex const *R, int shift,
+                      float complex *S);
+int ko_channel_block_realout(int in_type, int m_bins, float complex const *X, int points, float complex const *R,
+                             int shift, float *full);
+
+/* fine-tuning oscillator (osc.h:12-19, osc.c:18-70) and the per-block logic of radio.c:1476-1501, :1515-1520 */
+struct ko_osc {
+  double freq, rate;
+  double complex phasor, phasor_step, phasor_step_step;
+  int steps;
+};
+void ko_osc_set(struct ko_osc *o, double f, double r);
+double complex ko_osc_step(struct ko_osc *o);
+struct ko_finetune {
+  struct ko_osc fine;
+  double remainder;
+  int bin_shift;
+  double complex phase_adjust;
+};
+void ko_finetune_init(struct ko_finetune *s);
+double ko_finetune_block(struct ko_finetune *s, int L, int M, int shift, double remainder, double out_samprate,
+                         double doppler_rate, float complex *y, int olen); /* returns bb_power */
+
+/* noise density estimate from the master spectrum (radio.c:1783-1866; quantile :1722-1775) */
+double ko_estimate_noise(int in_type, int m_bins, float complex const *X, int s_bins, int shift, double samprate);
+
 #ifdef __cplusplus
 }
 #endif

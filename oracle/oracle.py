@@ -58,6 +58,18 @@ def lib() -> C.CDLL:
         L.ko_siggen_complex.argtypes = [C.c_void_p, _c64p, C.c_long, C.c_double, C.c_double, C.c_double]
         L.ko_siggen_tones_i16.argtypes = [_i16p, C.c_long, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_uint64]
         L.ko_compute_tuning.argtypes = [C.c_int, C.c_double, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.ko_channel_block_beam.argtypes = [C.c_int, _c64p, C.c_int, _c64p, C.c_int] + [C.c_double] * 4 + [_c64p]
+        L.ko_channel_block_realout.argtypes = [C.c_int, C.c_int, _c64p, C.c_int, _c64p, C.c_int, _f32p]
+        L.ko_slice_realout.argtypes = [C.c_int, C.c_int, _c64p, C.c_int, _c64p, C.c_int, _c64p]
+        L.ko_slice_realout.restype = None
+        L.ko_finetune_init.argtypes = [C.c_void_p]
+        L.ko_finetune_init.restype = None
+        L.ko_finetune_block.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _c64p, C.c_int]
+        L.ko_finetune_block.restype = C.c_double
+        L.ko_osc_set.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.ko_osc_set.restype = None
+        L.ko_estimate_noise.argtypes = [C.c_int, C.c_int, _c64p, C.c_int, C.c_int, C.c_double]
+        L.ko_estimate_noise.restype = C.c_double
         _lib = L
     return _lib
 
@@ -154,6 +166,64 @@ def compute_tuning(N, samprate, freq):
     sh, rem = C.c_int(0), C.c_double(0)
     r = lib().ko_compute_tuning(N, samprate, freq, C.byref(sh), C.byref(rem))
     return r, sh.value, rem.value
+
+
+def channel_block_beam(spectrum, response, shift, i_weight=1.0, q_weight=0.0) -> np.ndarray:
+    """COMPLEX master, beam == true (filter.c:756-775); weights as set_filter_weights takes them (filter.c:922-929)."""
+    alpha = 0.5 * complex(i_weight) - 1j * complex(q_weight)
+    beta = 0.5 * complex(i_weight) + 1j * complex(q_weight)
+    out = np.empty(len(response), np.complex64)
+    lib().ko_channel_block_beam(len(spectrum), np.ascontiguousarray(spectrum, np.complex64), len(response),
+                                np.ascontiguousarray(response, np.complex64), int(shift),
+                                alpha.real, alpha.imag, beta.real, beta.imag, out)
+    return out
+
+
+def channel_block_realout(in_type, spectrum, response, shift) -> np.ndarray:
+    """REAL-output slave (filter.c:794-809 + c2r inverse): all `points` real samples; user part = last olen."""
+    pts = len(response)
+    out = np.empty(pts, np.float32)
+    r = lib().ko_channel_block_realout(in_type, len(spectrum), np.ascontiguousarray(spectrum, np.complex64), pts,
+                                       np.ascontiguousarray(response, np.complex64), int(shift), out)
+    if r != 0:
+        raise ValueError("REAL-output slaves need an even number of points")
+    return out
+
+
+def design_response_realout(points, olen, master_points, master_real, low, high, beta) -> np.ndarray:
+    """set_filter for a REAL slave folds both edges to positive frequencies first (filter.c:971-975)."""
+    return design_response(points, olen, master_points, master_real, abs(low), abs(high), beta)
+
+
+def estimate_noise(in_type, spectrum, s_bins, shift, samprate) -> float:
+    """radio.c:1783-1866 on one block's master spectrum."""
+    return float(lib().ko_estimate_noise(in_type, len(spectrum), np.ascontiguousarray(spectrum, np.complex64),
+                                         int(s_bins), int(shift), float(samprate)))
+
+
+class FineTune:
+    """Per-channel state of radio.c:1476-1501 (fine oscillator, block phase) + :1515-1520 (power)."""
+
+    class _S(C.Structure):
+        _fields_ = [("freq", C.c_double), ("rate", C.c_double), ("phasor", C.c_double * 2), ("phasor_step", C.c_double * 2),
+                    ("phasor_step_step", C.c_double * 2), ("steps", C.c_int), ("remainder", C.c_double),
+                    ("bin_shift", C.c_int), ("phase_adjust", C.c_double * 2)]
+
+    def __init__(self, L, M, out_samprate):
+        self.s = self._S()
+        lib().ko_finetune_init(C.byref(self.s))
+        self.L, self.M, self.rate = L, M, float(out_samprate)
+
+    def block(self, y: np.ndarray, shift: int, remainder: float, doppler_rate: float = 0.0):
+        """Rotates y (complex64, olen samples) in place; returns bb_power."""
+        assert y.dtype == np.complex64 and y.flags.c_contiguous
+        return float(lib().ko_finetune_block(C.byref(self.s), self.L, self.M, int(shift), float(remainder), self.rate,
+                                             float(doppler_rate), y, len(y)))
+
+    @property
+    def phase_cycles(self) -> float:
+        """current oscillator phase in cycles"""
+        return float(np.angle(complex(*self.s.phasor)) / (2 * np.pi))
 
 
 class Notches:
@@ -357,3 +427,84 @@ def ref_siggen_complex(n, amplitude, noise, cycles_per_sample, scale) -> np.ndar
     out = np.empty(n, np.complex64)
     ref_lib().ref_siggen_complex(out, n, amplitude, noise, cycles_per_sample, scale, 1)
     return out
+
+
+# ------------------------------------------------------------------ the reference's downconvert() --
+_radio = None
+
+
+def radio_available() -> bool:
+    build()
+    return (HERE / "_ref/libka9qradio.so").exists()
+
+
+def radio_lib() -> C.CDLL:
+    """oracle/_ref/libka9qradio.so: the reference's radio.c (downconvert, estimate_noise, compute_tuning) unmodified."""
+    global _radio
+    if _radio is None:
+        build()
+        p = HERE / "_ref/libka9qradio.so"
+        if not p.exists():
+            raise FileNotFoundError("oracle/_ref/libka9qradio.so not built (needs /root/reference)")
+        R = C.CDLL(str(p))
+        R.rr_open.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+        R.rr_add_channel.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
+        R.rr_set_freq.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
+        R.rr_write_real.argtypes = [_f32p, C.c_int]
+        R.rr_write_complex.argtypes = [_c64p, C.c_int]
+        R.rr_downconvert.argtypes = [C.c_int, _c64p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                     C.POINTER(C.c_double)]
+        R.rr_get_spectrum.argtypes = [_c64p]
+        R.rr_osc_run.argtypes = [C.c_double, C.c_double, C.c_long, C.c_void_p]
+        R.rr_osc_run.restype = None
+        R.rr_close.restype = None
+        _radio = R
+    return _radio
+
+
+class RadioRef:
+    """One front end + channels run through the reference's own downconvert() (radio.c:1410)."""
+
+    def __init__(self, L, M, in_type, samprate, frequency=0.0):
+        self.R = radio_lib()
+        if self.R.rr_open(L, M, in_type, samprate, frequency) != 0:
+            raise RuntimeError("rr_open failed (one session at a time)")
+        self.in_type, self.olen = in_type, []
+
+    def add_channel(self, olen, out_samprate, freq, low, high, beta) -> int:
+        i = self.R.rr_add_channel(olen, out_samprate, freq, low, high, beta)
+        if i < 0:
+            raise RuntimeError("rr_add_channel failed")
+        self.olen.append(olen)
+        return i
+
+    def set_freq(self, ch, freq, doppler=0.0, doppler_rate=0.0):
+        self.R.rr_set_freq(ch, freq, doppler, doppler_rate)
+
+    def write(self, x) -> int:
+        if self.in_type == KO_REAL:
+            return self.R.rr_write_real(np.ascontiguousarray(x, np.float32), len(x))
+        return self.R.rr_write_complex(np.ascontiguousarray(x, np.complex64), len(x))
+
+    def spectrum(self) -> np.ndarray:
+        out = np.empty(self.R.rr_master_bins(), np.complex64)
+        self.R.rr_get_spectrum(out)
+        return out
+
+    def downconvert(self, ch):
+        """-> dict(baseband, bb_power, n0, shift, remainder)"""
+        y = np.empty(self.olen[ch], np.complex64)
+        p, n0, rem, sh = C.c_double(0), C.c_double(0), C.c_double(0), C.c_int(0)
+        r = self.R.rr_downconvert(ch, y, C.byref(p), C.byref(n0), C.byref(sh), C.byref(rem))
+        if r != 0:
+            raise RuntimeError("downconvert returned %d" % r)
+        return dict(baseband=y, bb_power=p.value, n0=n0.value, shift=sh.value, remainder=rem.value)
+
+    def close(self):
+        self.R.rr_close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
