@@ -27,7 +27,9 @@ enum kgpu_format {
   KGPU_FMT_I16 = 1  /* raw int16 samples / int16 I/Q pairs: the fused ingest (rx888.c:753-767) */
 };
 enum kgpu_chan_flags {
-  KGPU_CHAN_ISB = 1 /* filter_out.isb, filter.c:895-909 */
+  KGPU_CHAN_ISB = 1, /* filter_out.isb, filter.c:895-909 */
+  KGPU_CHAN_BEAM = 4 /* filter_out.beam on a COMPLEX master, filter.c:756-775; weights: kgpu_bank_set_weights */
+  /* 2 (REAL output) and 8 (oscillator) are owned by kgpu_bank_define_ex / kgpu_bank_set_osc */
 };
 
 typedef struct kgpu_master kgpu_master; /* geometry + plans of one struct filter_in */
@@ -86,6 +88,10 @@ void kgpu_bank_destroy(kgpu_bank *b);
 /* (Re)define channel idx: olen output samples per block (points = olen*N/L must be integral,
  * filter.c:312-316), COMPLEX output.  Returns points, or -1. */
 int kgpu_bank_define(kgpu_bank *b, int idx, int olen);
+/* Same with the output type of create_filter_output (filter.c:345-392): KGPU_COMPLEX, or KGPU_REAL for the
+ * REAL-output slaves of wfm.c:76 / stereod.c:387 (slice filter.c:794-809, c2r inverse filter.c:386,914): olen FLOATS
+ * per block, packed into (olen+1)/2 float2 of the output row.  points must be even for KGPU_REAL. */
+int kgpu_bank_define_ex(kgpu_bank *b, int idx, int olen, int out_type);
 /* set_filter (filter.c:968-1045): Kaiser-windowed sinc designed on the host in double, forward
  * transformed on the device.  low/high are fractions of the output rate. */
 int kgpu_bank_set_filter(kgpu_bank *b, int idx, double low, double high, double kaiser_beta);
@@ -96,14 +102,39 @@ int kgpu_bank_get_response(kgpu_bank *b, int idx, float *response); /* device ->
 int kgpu_bank_set_shift(kgpu_bank *b, int idx, int shift);
 int kgpu_bank_set_flags(kgpu_bank *b, int idx, int flags);
 int kgpu_bank_enable(kgpu_bank *b, int idx, int enabled);
+/* Beam weights alpha, beta as set_filter_weights leaves them in struct filter_out (filter.c:922-929):
+ * alpha = i_weight/2 - j q_weight, beta = i_weight/2 + j q_weight.  Used when KGPU_CHAN_BEAM is set. */
+int kgpu_bank_set_weights(kgpu_bank *b, int idx, double alpha_re, double alpha_im, double beta_re, double beta_im);
+/* Fine-tuning oscillator fused into the channel kernel's store (replaces the per-sample loop radio.c:1499-1501 with
+ * step_osc, osc.c:60-70, and the block phase of radio.c:1491-1497).  Output sample n of the k-th block processed after
+ * this call is multiplied by exp(2 pi j (phase + (k+1) block_adj + m freq + rate m (m+1) / 2)), m = k*olen + n.
+ * phase in cycles, freq in cycles/sample (= -remainder / output rate, radio.c:1481), rate in cycles/sample^2
+ * (doppler_rate / rate^2), block_adj in cycles (= (shift % V) / V, radio.c:1493).  enable = 0 switches it off.
+ * With the oscillator on, kgpu_bank_run_ex also writes the block's mean |y|^2 (radio.c:1515-1520). */
+int kgpu_bank_set_osc(kgpu_bank *b, int idx, int enable, double phase_cycles, double freq_cps, double rate_cps2,
+                      double block_adj_cycles);
+/* Phase (cycles, [0,1)) the oscillator will have at the first sample of the next block, before that block's adjustment. */
+int kgpu_bank_get_osc_phase(kgpu_bank *b, int idx, double *phase_cycles);
+/* Index of the block the next run processes (advanced by every kgpu_bank_run*; the filter.h layer sets it to the job number). */
+int kgpu_bank_set_block_counter(kgpu_bank *b, long counter);
+long kgpu_bank_block_counter(kgpu_bank const *b);
 int kgpu_bank_channels(kgpu_bank const *b);          /* highest defined idx + 1 */
 long kgpu_bank_out_stride(kgpu_bank const *b);        /* float2 per block of the packed output row */
 long kgpu_bank_out_offset(kgpu_bank const *b, int idx); /* float2 offset of channel idx inside a row */
 /* Batched slice x response -> inverse transform -> keep last olen (filter.c:728-921) for every
  * enabled channel and `nblocks` spectra.  d_out: nblocks * out_stride float2. */
 int kgpu_bank_run(kgpu_bank *b, const void *d_spec, int nblocks, void *d_out, void *stream);
+/* Same, plus out_pitch: float2 between consecutive blocks' output rows (0 = packed, kgpu_bank_out_stride), and
+ * d_power: NULL or nblocks * capacity floats; [block*capacity + idx] receives the mean |y|^2 of every channel whose
+ * oscillator is on (chan->sig.bb_power, radio.c:1515-1520). */
+int kgpu_bank_run_ex(kgpu_bank *b, const void *d_spec, int nblocks, void *d_out, long out_pitch, float *d_power, void *stream);
 /* Single channel, single block (the retune slow path of the filter.h layer). d_out: olen float2. */
 int kgpu_bank_run_one(kgpu_bank *b, int idx, const void *d_spec, void *d_out, void *stream);
+int kgpu_bank_run_one_ex(kgpu_bank *b, int idx, const void *d_spec, void *d_out, float *d_power /* NULL or 1 float */, void *stream);
+/* Noise density estimate per channel and block from the device-resident spectrum (estimate_noise, radio.c:1783-1866,
+ * quantile :1722-1775) with the shift each channel was last given: d_n0[block*capacity + idx], doubles, in the
+ * reference's scaling (energy per bin / (bins * samprate)).  Saves the 13 MB/block spectrum read-back. */
+int kgpu_bank_noise(kgpu_bank *b, const void *d_spec, int nblocks, double samprate, double *d_n0, void *stream);
 
 /* Push pending channel changes (shift/filter/enable) to the device now, ordered after `stream`. */
 int kgpu_bank_commit(kgpu_bank *b, void *stream);

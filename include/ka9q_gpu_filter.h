@@ -124,8 +124,24 @@ int write_rfilter(struct filter_in *master, float const *samples, int n);
 /* EXTENSION: raw ADC words.  n int16 samples (REAL master) or n I/Q pairs (COMPLEX master); a
  * master fed this way must not also be fed through write_rfilter/write_cfilter. */
 int write_i16filter(struct filter_in *master, int16_t const *samples, int n, float scale, bool derandomize);
-/* EXTENSION: serve many slaves with one call (what 1024 channel threads would each do). */
+/* Where a driver may deposit the next raw samples itself (pinned, mirrored ring: a block's worth stays contiguous),
+ * e.g. as the libusb transfer buffer of rx888.c:797-826; publish with write_i16filter(master, NULL, n, scale, derand). */
+int16_t *filter_i16_write_pointer(struct filter_in *master);
+/* EXTENSION: serve many slaves with one call (what 1024 channel threads would each do): one wait per block. */
 int execute_filter_output_batch(struct filter_out *const *slaves, int const *shifts, int n);
+/* EXTENSION (downconvert()'s per-sample work, radio.c:1476-1501 and :1515-1520, on the device): execute_filter_output
+ * plus the fine-tuning oscillator (set_osc / step_osc, osc.c:28-70), the block phase correction for shifts that are
+ * not multiples of the overlap factor, and the baseband power.  shift, remainder: compute_tuning's results
+ * (radio.c:1175-1199); samprate: the slave's output rate; doppler_rate: Hz/s.  *bb_power = chan->sig.bb_power.
+ * output.c then holds what radio.c:1499-1501 would have left there; the caller skips that loop. */
+int execute_filter_output_tuned(struct filter_out *slave, int shift, double remainder, double samprate, double doppler_rate,
+                                double *bb_power);
+int filter_output_untune(struct filter_out *slave); /* back to plain execute_filter_output semantics */
+/* EXTENSION (estimate_noise, radio.c:1783-1866, on the device): once enabled (samprate = Frontend.samprate), every block
+ * carries one noise-density estimate per slave; filter_noise_estimate() returns the one belonging to the block the
+ * slave's last execute_filter_output* delivered (NAN if that block had to be recomputed alone after a retune). */
+int filter_input_enable_noise(struct filter_in *master, double samprate);
+double filter_noise_estimate(struct filter_out const *slave);
 
 /* housekeeping the reference exports from filter.c */
 void *run_fft(void *);

@@ -17,6 +17,7 @@ LIB_PATH = PKG / "libka9qgpu.so"
 KGPU_COMPLEX, KGPU_REAL = 1, 2
 KGPU_FMT_F32, KGPU_FMT_I16 = 0, 1
 KGPU_CHAN_ISB = 1
+KGPU_CHAN_BEAM = 4
 
 _lib = None
 
@@ -74,6 +75,16 @@ def load() -> C.CDLL:
     L.kgpu_bank_run.argtypes = [vp, vp, i, vp, vp]
     L.kgpu_bank_run_one.argtypes = [vp, i, vp, vp, vp]
     L.kgpu_bank_commit.argtypes = [vp, vp]
+    L.kgpu_bank_define_ex.argtypes = [vp, i, i, i]
+    L.kgpu_bank_set_weights.argtypes = [vp, i, d, d, d, d]
+    L.kgpu_bank_set_osc.argtypes = [vp, i, i, d, d, d, d]
+    L.kgpu_bank_get_osc_phase.argtypes = [vp, i, vp]
+    L.kgpu_bank_set_block_counter.argtypes = [vp, l]
+    L.kgpu_bank_block_counter.argtypes = [vp]
+    L.kgpu_bank_block_counter.restype = l
+    L.kgpu_bank_run_ex.argtypes = [vp, vp, i, vp, l, vp, vp]
+    L.kgpu_bank_run_one_ex.argtypes = [vp, i, vp, vp, vp, vp]
+    L.kgpu_bank_noise.argtypes = [vp, vp, i, d, vp, vp]
     L.kgpu_use_static_kernels.argtypes = [i]
     L.kgpu_set_tuning.argtypes = [i, i]
     L.kgpu_set_debug_buffer.argtypes = [vp]
@@ -182,8 +193,33 @@ class Bank:
         if not self.h:
             raise KgpuError("kgpu_bank_create: " + self.lib.kgpu_last_error().decode())
 
-    def define(self, idx, olen) -> int:
-        return check(self.lib.kgpu_bank_define(self.h, idx, olen), "kgpu_bank_define")
+    def define(self, idx, olen, out_type=KGPU_COMPLEX) -> int:
+        return check(self.lib.kgpu_bank_define_ex(self.h, idx, olen, out_type), "kgpu_bank_define_ex")
+
+    def set_weights(self, idx, i_weight=1.0, q_weight=0.0):
+        """set_filter_weights (filter.c:922-929)"""
+        a = 0.5 * complex(i_weight) - 1j * complex(q_weight)
+        b = 0.5 * complex(i_weight) + 1j * complex(q_weight)
+        check(self.lib.kgpu_bank_set_weights(self.h, idx, a.real, a.imag, b.real, b.imag), "kgpu_bank_set_weights")
+
+    def set_osc(self, idx, enable, phase=0.0, freq=0.0, rate=0.0, block_adj=0.0):
+        check(self.lib.kgpu_bank_set_osc(self.h, idx, int(enable), phase, freq, rate, block_adj), "kgpu_bank_set_osc")
+
+    def osc_phase(self, idx) -> float:
+        v = C.c_double(0)
+        check(self.lib.kgpu_bank_get_osc_phase(self.h, idx, C.cast(C.pointer(v), C.c_void_p)), "kgpu_bank_get_osc_phase")
+        return v.value
+
+    @property
+    def block_counter(self) -> int:
+        return self.lib.kgpu_bank_block_counter(self.h)
+
+    @block_counter.setter
+    def block_counter(self, v: int):
+        check(self.lib.kgpu_bank_set_block_counter(self.h, int(v)), "kgpu_bank_set_block_counter")
+
+    def noise(self, d_spec: int, nblocks: int, samprate: float, d_n0: int, stream: int = 0):
+        check(self.lib.kgpu_bank_noise(self.h, d_spec, nblocks, samprate, d_n0, stream or None), "kgpu_bank_noise")
 
     def set_filter(self, idx, low, high, beta):
         check(self.lib.kgpu_bank_set_filter(self.h, idx, low, high, beta), "kgpu_bank_set_filter")
@@ -217,8 +253,8 @@ class Bank:
     def out_offset(self, idx) -> int:
         return self.lib.kgpu_bank_out_offset(self.h, idx)
 
-    def run(self, d_spec: int, nblocks: int, d_out: int, stream: int = 0):
-        check(self.lib.kgpu_bank_run(self.h, d_spec, nblocks, d_out, stream or None), "kgpu_bank_run")
+    def run(self, d_spec: int, nblocks: int, d_out: int, stream: int = 0, d_power: int = 0):
+        check(self.lib.kgpu_bank_run_ex(self.h, d_spec, nblocks, d_out, 0, d_power or None, stream or None), "kgpu_bank_run")
 
     def run_one(self, idx, d_spec: int, d_out: int, stream: int = 0):
         check(self.lib.kgpu_bank_run_one(self.h, idx, d_spec, d_out, stream or None), "kgpu_bank_run_one")

@@ -24,11 +24,16 @@ class Channelizer:
         self.L, self.M, self.N, self.in_type = L, M, L + M - 1, in_type
         self.nchan = 0
         self._olen = {}
+        self._real = {}
+        self._tune = {}
+        self.capacity = capacity
 
     # ---- channel management (create_filter_output + set_filter + shift) -------------------
-    def add_channel(self, olen, shift, low=None, high=None, beta=None, response=None, isb=False) -> int:
+    def add_channel(self, olen, shift, low=None, high=None, beta=None, response=None, isb=False, out_type=capi.KGPU_COMPLEX,
+                    beam=None) -> int:
+        """out_type KGPU_REAL: REAL-output slave (olen floats per block); beam=(i_weight, q_weight): beam synthesis."""
         idx = self.nchan
-        pts = self.bank.define(idx, olen)
+        pts = self.bank.define(idx, olen, out_type)
         if response is not None:
             self.bank.set_response(idx, response)
         else:
@@ -36,9 +41,39 @@ class Channelizer:
         self.bank.set_shift(idx, shift)
         if isb:
             self.bank.set_flags(idx, capi.KGPU_CHAN_ISB)
+        if beam is not None:
+            self.bank.set_weights(idx, beam[0], beam[1])
+            self.bank.set_flags(idx, capi.KGPU_CHAN_BEAM)
         self._olen[idx] = (olen, pts)
+        self._real[idx] = out_type == capi.KGPU_REAL
         self.nchan += 1
         return idx
+
+    def tune(self, idx: int, shift: int, remainder: float, out_samprate: float, doppler_rate: float = 0.0) -> None:
+        """Fine tuning fused into the channel kernel: the bookkeeping of radio.c:1476-1497 (set_osc on a new
+        remainder, per-block phase step (shift % V)/V, one-time phase term on a shift change) expressed as
+        kgpu_bank_set_osc parameters.  Call before channels() whenever compute_tuning's (shift, remainder) may
+        have moved; a call with unchanged values is free."""
+        import math
+
+        st = self._tune.setdefault(idx, dict(bin_shift=-1000999, remainder=float("nan"), freq=0.0, rate=0.0, adj=0.0, on=False))
+        changed, jump = False, 0.0
+        if shift != st["bin_shift"] or math.isnan(st["remainder"]) or remainder != st["remainder"]:
+            st["freq"] = -remainder / out_samprate                      # radio.c:1481
+            st["rate"] = doppler_rate / (out_samprate * out_samprate)
+            st["remainder"] = remainder
+            changed = True
+        if shift != st["bin_shift"]:
+            V = 1 + self.L // (self.M - 1)                               # radio.c:1492
+            st["adj"] = math.fmod(shift, V) / V                          # cispi(2 (shift % V) / V), C remainder
+            jump = math.fmod((shift - st["bin_shift"]) / (-2.0 * (V - 1)) / 2.0, 1.0)  # radio.c:1494 in cycles
+            st["bin_shift"] = shift
+            self.bank.set_shift(idx, shift)
+            changed = True
+        if changed:
+            phase = self.bank.osc_phase(idx) if st["on"] else 0.0       # set_osc starts an uninitialised phasor at 1
+            self.bank.set_osc(idx, True, phase + jump, st["freq"], st["rate"], st["adj"])
+            st["on"] = True
 
     # ---- data movement helpers -------------------------------------------------------------
     def stage_stream(self, samples: np.ndarray) -> torch.Tensor:
@@ -77,13 +112,27 @@ class Channelizer:
         st = torch.cuda.current_stream(self.device).cuda_stream
         self.master.apply_notches(spectra.data_ptr(), nblocks, st)
 
-    def channels(self, spectra: torch.Tensor, nblocks: int, outputs: torch.Tensor) -> None:
+    def channels(self, spectra: torch.Tensor, nblocks: int, outputs: torch.Tensor, power: torch.Tensor | None = None) -> None:
+        """power: optional float32 [nblocks, capacity]; channels whose oscillator is on get their block power there."""
         st = torch.cuda.current_stream(self.device).cuda_stream
-        self.bank.run(spectra.data_ptr(), nblocks, outputs.data_ptr(), st)
+        self.bank.run(spectra.data_ptr(), nblocks, outputs.data_ptr(), st, power.data_ptr() if power is not None else 0)
+
+    def alloc_power(self, nblocks) -> torch.Tensor:
+        return torch.zeros((nblocks, self.capacity), dtype=torch.float32, device=self.device)
+
+    def noise(self, spectra: torch.Tensor, nblocks: int, samprate: float) -> torch.Tensor:
+        """N0 per block and channel (estimate_noise, radio.c:1783-1866) -> float64 [nblocks, capacity]"""
+        n0 = torch.zeros((nblocks, self.capacity), dtype=torch.float64, device=self.device)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        self.bank.noise(spectra.data_ptr(), nblocks, samprate, n0.data_ptr(), st)
+        return n0
 
     def channel_slice(self, outputs: torch.Tensor, idx: int) -> torch.Tensor:
         off = self.bank.out_offset(idx)
-        return outputs[:, off:off + self._olen[idx][0]]
+        olen = self._olen[idx][0]
+        if self._real.get(idx):  # olen floats packed into (olen+1)/2 complex slots
+            return torch.view_as_real(outputs[:, off:off + (olen + 1) // 2]).reshape(outputs.shape[0], -1)[:, :olen]
+        return outputs[:, off:off + olen]
 
     def close(self):
         self.bank.close()

@@ -16,6 +16,7 @@
 #include "../../include/ka9q_gpu.h"
 #include "chan_kernels.cuh"
 #include "fwd_kernels.cuh"
+#include "noise_kernel.cuh"
 #include "plan.cuh"
 #include "static_kernels.cuh"
 #include "static_kernels_v2.cuh"
@@ -84,8 +85,8 @@ static int fail(char const *fmt, ...) {
 // ------------------------------------------------------------------ per-launch profiling -----
 // When enabled, every kernel launch is bracketed by CUDA events on the launching stream; bench.py
 // reads the per-kernel totals for its roofline line (events are markers, they do not serialise).
-enum KernelId { K_FWD_COLS = 0, K_FWD_ROWS, K_CHAN, K_NOTCH, K_RESPONSE, K_COUNT };
-static char const *const kKernelNames[K_COUNT] = {"fwd_cols", "fwd_rows", "chan", "notch", "response_fft"};
+enum KernelId { K_FWD_COLS = 0, K_FWD_ROWS, K_CHAN, K_NOTCH, K_RESPONSE, K_NOISE, K_COUNT };
+static char const *const kKernelNames[K_COUNT] = {"fwd_cols", "fwd_rows", "chan", "notch", "response_fft", "noise"};
 struct ProfRec {
   cudaEvent_t a, b;
   int kid;
@@ -467,7 +468,7 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
       for (int r = 0; r < 64; r++) tB64[(size_t)c * 64 + r] = root(c * r, m->nc);
     }
     if (m->static_cols == 1296) {  // inter-pass factors in the v2 kernel's (u, t2) split
-      std::vector<float2> tU((size_t)(n2 + 8) * 144, make_float2(0.f, 0.f)), tT((size_t)(n2 + 8) * 9 + 16, make_float2(0.f, 0.f));
+      std::vector<float2> tU((size_t)(n2 + 8) * 144, make_float2(0.f, 0.f)), tT((size_t)(n2 + 16) * 9 + 32, make_float2(0.f, 0.f));
       for (long c = 0; c < n2; c++) {
         for (int u = 0; u < 144; u++) tU[(size_t)c * 144 + u] = root(c * (u / 12 + 12 * (u % 12)), m->nc);
         for (int t = 0; t < 9; t++) tT[(size_t)c * 9 + t] = root(c * 144 * t, m->nc);
@@ -501,6 +502,8 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
         set_smem((const void *)fwd_rows_v2<true, 1296, true>, sv2) || set_smem((const void *)fwd_rows_v2<true, 1296, true, true>, sv2) ||
         set_smem((const void *)fwd_cols_v2<0, 1250, 0, true>, sv1 + 128) || set_smem((const void *)fwd_cols_v2<1, 1250, 0, true>, sv1 + 128) ||
         set_smem((const void *)fwd_cols_v2<2, 1250, 0, true>, sv1 + 128) ||
+        set_smem((const void *)fwd_cols_v2<1, 1250, 0, false, 16>, sizeof(float2) * (16 * 1297 + 1288 + 160)) ||
+        set_smem((const void *)fwd_cols_v2<1, 1250, 0, false, 6>, sizeof(float2) * (6 * 1298 + 1288 + 60)) ||
         set_smem((const void *)fwd_cols_v3<1, 1250>, sv1) || set_smem((const void *)fwd_cols_v3<2, 1250>, sv1) ||
         set_smem((const void *)fwd_rows_v3<true, 1296, true>, sv3) || set_smem((const void *)fwd_rows_v3<false, 1296, false>, sv3) ||
         set_smem((const void *)fwd_rows_v3<true, 0, false>, sv3) || set_smem((const void *)fwd_rows_v3<false, 0, false>, sv3) || set_smem((const void *)fwd_rows_v2<false, 1296, false>, sv2) ||
@@ -646,6 +649,14 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
         int const grid = std::min(2 * sm_count(), ntiles);
         if (f == 1) fwd_cols_v3<1, 1250><<<grid, 288, sv1, st>>>(a1, t2, tpb, ntiles);
         else fwd_cols_v3<2, 1250><<<grid, 288, sv1, st>>>(a1, t2, tpb, ntiles);
+      } else if (m->sp.n2 == 1250 && f == 1 && g_tuning[13].load() == 2) {  // 6-column tiles, three CTAs per SM
+        size_t const sv6 = sizeof(float2) * (6 * 1298 + 1288 + 60);
+        dim3 const g6((unsigned)((m->sp.n2 + 5) / 6), (unsigned)nblocks);
+        fwd_cols_v2<1, 1250, 0, false, 6><<<g6, 216, sv6, st>>>(a1, t2, m->mid_map);
+      } else if (m->sp.n2 == 1250 && f == 1 && g_tuning[13].load() == 1) {  // 16-column tiles, one CTA per SM
+        size_t const sv16 = sizeof(float2) * (16 * 1297 + 1288 + 160);
+        dim3 const g16((unsigned)((m->sp.n2 + 15) / 16), (unsigned)nblocks);
+        fwd_cols_v2<1, 1250, 0, false, 16><<<g16, 576, sv16, st>>>(a1, t2, m->mid_map);
       } else if (m->sp.n2 == 1250) {
         if (f == 0) fwd_cols_v2<0, 1250><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
         else if (f == 1 && g_tuning[2].load() == 1) fwd_cols_v2<1, 1250, 1><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
@@ -893,8 +904,10 @@ int design_taps(int points, int olen, int master_points, bool master_real, doubl
 // ------------------------------------------------------------------ bank --------------------
 struct ChanHost {
   bool defined = false, enabled = false, has_response = false;
+  bool real_out = false;  // REAL-output slave (filter.c:370-390): olen floats per block
   int olen = 0, points = 0, plan = -1, shift = 0, flags = 0;
   long resp_off = 0;
+  ChanAux aux{};          // oscillator / beam parameters (zero = unused)
 };
 struct kgpu_bank {
   kgpu_master *m;
@@ -911,9 +924,16 @@ struct kgpu_bank {
   int max_points = 0;
   struct Group {
     int plan, points, off, count;
+    bool generic;  // REAL-output / beam channels: served by the runtime-plan kernel only
   };
   std::vector<Group> groups;  // enabled channels grouped by inverse-transform plan
   int *d_order = nullptr;
+  ChanAux *d_aux = nullptr;   // [capacity]
+  int *d_shift = nullptr;     // [capacity] shifts, for the noise estimator
+  std::vector<ChanAux> aux;
+  long block_counter = 0;     // index of the next block a run will process (oscillator epoch arithmetic)
+  long last_rebase = 0;
+  bool any_osc = false;
 };
 
 static void resolve_walk(kgpu_master const *m, ChanHost const &c, ChanDesc &d) {
@@ -923,6 +943,11 @@ static void resolve_walk(kgpu_master const *m, ChanHost const &c, ChanDesc &d) {
   d.ncopy = 0;
   d.q0 = 0;
   d.dir = 1;
+  if (c.real_out) {  // filter.c:794-809: the kernel indexes the master by si + shift itself
+    d.q0 = (int)shift;
+    d.ncopy = 1;
+    return;
+  }
   if (m->in_type == KGPU_REAL) {
     if (shift >= 0) {  // filter.c:819-855
       long const start = shift - half;
@@ -974,10 +999,12 @@ static int bank_commit(kgpu_bank *b, cudaStream_t st) {
     if (!c.defined) continue;
     d.points = c.points;
     d.olen = c.olen;
-    d.flags = c.flags;
+    d.flags = (c.flags & (kChanIsb | kChanBeam | kChanOsc)) | (c.real_out ? kChanRealOut : 0);
+    if (c.real_out) d.flags &= ~(kChanIsb | kChanBeam | kChanOsc);  // the reference applies none of them to REAL slaves
+    if (b->m->in_type != KGPU_COMPLEX) d.flags &= ~kChanBeam;       // beam exists for COMPLEX masters only (filter.c:756)
     d.resp_off = c.resp_off;
     d.out_off = off;
-    off += c.olen;
+    off += c.real_out ? (c.olen + 1) / 2 : c.olen;
     if (c.enabled && c.has_response) {
       d.plan = c.plan;
       resolve_walk(b->m, c, d);
@@ -988,19 +1015,46 @@ static int bank_commit(kgpu_bank *b, cudaStream_t st) {
   // one launch per distinct plan: order[] lists that plan's descriptors
   std::vector<int> order;
   b->groups.clear();
+  auto generic_only = [&](int i) { return (b->desc[(size_t)i].flags & (kChanRealOut | kChanBeam)) != 0; };
   for (int i = 0; i < b->nchan; i++) {
     if (b->desc[(size_t)i].plan < 0) continue;
+    bool const gen = generic_only(i);
     bool found = false;
     for (auto &g : b->groups)
-      if (g.plan == b->desc[(size_t)i].plan) found = true;
+      if (g.plan == b->desc[(size_t)i].plan && g.generic == gen) found = true;
     if (found) continue;
-    kgpu_bank::Group g{b->desc[(size_t)i].plan, b->desc[(size_t)i].points, (int)order.size(), 0};
+    kgpu_bank::Group g{b->desc[(size_t)i].plan, b->desc[(size_t)i].points, (int)order.size(), 0, gen};
     for (int k = i; k < b->nchan; k++)
-      if (b->desc[(size_t)k].plan == g.plan) order.push_back(k);
+      if (b->desc[(size_t)k].plan == g.plan && generic_only(k) == gen) order.push_back(k);
     g.count = (int)order.size() - g.off;
     b->groups.push_back(g);
   }
+  // oscillator epochs move up to the current block so the device-side phase arithmetic stays small
+  b->any_osc = false;
+  b->aux.assign((size_t)std::max(b->nchan, 1), ChanAux{});
+  for (int i = 0; i < b->nchan; i++) {
+    ChanHost &c = b->ch[(size_t)i];
+    if (c.defined && (c.flags & kChanOsc) && !c.real_out) {
+      b->any_osc = true;
+      long const K = b->block_counter - c.aux.osc_epoch;
+      if (K > 0) {
+        double const D = (double)K * (double)c.olen;
+        double ph = c.aux.osc_phase + (double)K * c.aux.osc_adj + D * c.aux.osc_freq + 0.5 * D * (D + 1.0) * c.aux.osc_rate;
+        c.aux.osc_phase = ph - floor(ph);
+        c.aux.osc_freq += c.aux.osc_rate * D;
+        c.aux.osc_epoch = b->block_counter;
+      }
+    }
+    b->aux[(size_t)i] = c.aux;
+  }
+  b->last_rebase = b->block_counter;
   CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaMemcpy(b->d_aux, b->aux.data(), sizeof(ChanAux) * b->aux.size(), cudaMemcpyHostToDevice));
+  {
+    std::vector<int> sh((size_t)std::max(b->nchan, 1), 0);
+    for (int i = 0; i < b->nchan; i++) sh[(size_t)i] = b->ch[(size_t)i].shift;
+    CUDA_OK(cudaMemcpy(b->d_shift, sh.data(), sizeof(int) * sh.size(), cudaMemcpyHostToDevice));
+  }
   if (!order.empty())
     CUDA_OK(cudaMemcpy(b->d_order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(b->d_desc, b->desc.data(), sizeof(ChanDesc) * b->desc.size(), cudaMemcpyHostToDevice));
@@ -1019,6 +1073,8 @@ extern "C" kgpu_bank *kgpu_bank_create(kgpu_master *m, int capacity) {
   b->ch.resize((size_t)capacity);
   CUDA_OKP(cudaMalloc(&b->d_desc, sizeof(ChanDesc) * (size_t)capacity));
   CUDA_OKP(cudaMalloc(&b->d_order, sizeof(int) * (size_t)capacity));
+  CUDA_OKP(cudaMalloc(&b->d_aux, sizeof(ChanAux) * (size_t)capacity));
+  CUDA_OKP(cudaMalloc(&b->d_shift, sizeof(int) * (size_t)capacity));
   return b;
 }
 extern "C" void kgpu_bank_destroy(kgpu_bank *b) {
@@ -1026,18 +1082,28 @@ extern "C" void kgpu_bank_destroy(kgpu_bank *b) {
   cudaFree(b->d_resp);
   cudaFree(b->d_desc);
   cudaFree(b->d_order);
+  cudaFree(b->d_aux);
+  cudaFree(b->d_shift);
   delete b;
 }
 static bool bad_idx(kgpu_bank const *b, int idx) { return !b || idx < 0 || idx >= b->capacity; }
 
-extern "C" int kgpu_bank_define(kgpu_bank *b, int idx, int olen) {
+static int bank_define(kgpu_bank *b, int idx, int olen, bool real_out);
+extern "C" int kgpu_bank_define(kgpu_bank *b, int idx, int olen) { return bank_define(b, idx, olen, false); }
+extern "C" int kgpu_bank_define_ex(kgpu_bank *b, int idx, int olen, int out_type) {
+  if (out_type != KGPU_COMPLEX && out_type != KGPU_REAL) return fail("kgpu_bank_define_ex: out_type must be KGPU_COMPLEX or KGPU_REAL");
+  return bank_define(b, idx, olen, out_type == KGPU_REAL);
+}
+static int bank_define(kgpu_bank *b, int idx, int olen, bool real_out) {
   if (bad_idx(b, idx) || olen < 1) return fail("kgpu_bank_define: bad arguments");
   long const num = (long)olen * b->m->N;
   if (num % b->m->L) return fail("invalid output length %d for N=%d L=%d (filter.c:312-316)", olen, b->m->N, b->m->L);
   int const points = (int)(num / b->m->L);
+  if (real_out && (points & 1)) return fail("kgpu_bank_define: REAL-output slaves need an even number of points (got %d)", points);
   int const plan = get_tile_plan(points);
   if (plan < 0) return fail("kgpu_bank_define: %d-point inverse transform cannot be planned", points);
   ChanHost &c = b->ch[(size_t)idx];
+  c.real_out = real_out;
   if (!(c.defined && c.points == points)) {
     long const need = (points + 3) / 4 * 4;
     if (b->resp_used + need > b->resp_cap) {
@@ -1088,6 +1154,10 @@ extern "C" int kgpu_bank_set_filter(kgpu_bank *b, int idx, double low, double hi
   if (bad_idx(b, idx) || !b->ch[(size_t)idx].defined) return fail("kgpu_bank_set_filter: channel not defined");
   ChanHost &c = b->ch[(size_t)idx];
   std::vector<float2> taps;
+  if (c.real_out) {  // filter edges may not cross DC for a real output (filter.c:971-975)
+    low = fabs(low);
+    high = fabs(high);
+  }
   if (design_taps(c.points, c.olen, b->m->N, b->m->in_type == KGPU_REAL, low, high, kaiser_beta, taps))
     return fail("kgpu_bank_set_filter: rejected (NaN or M < 2), cf. filter.c:969,989");
   return upload_taps_and_transform(b, c, taps.data(), true);
@@ -1113,12 +1183,54 @@ extern "C" int kgpu_bank_set_shift(kgpu_bank *b, int idx, int shift) {
 }
 extern "C" int kgpu_bank_set_flags(kgpu_bank *b, int idx, int flags) {
   if (bad_idx(b, idx) || !b->ch[(size_t)idx].defined) return fail("kgpu_bank_set_flags: channel not defined");
+  int const keep = b->ch[(size_t)idx].flags & kChanOsc;  // the oscillator bit belongs to kgpu_bank_set_osc
+  flags = (flags & ~kChanOsc) | keep;
   if (b->ch[(size_t)idx].flags != flags) {
     b->ch[(size_t)idx].flags = flags;
     b->dirty = true;
   }
   return 0;
 }
+extern "C" int kgpu_bank_set_weights(kgpu_bank *b, int idx, double alpha_re, double alpha_im, double beta_re, double beta_im) {
+  if (bad_idx(b, idx) || !b->ch[(size_t)idx].defined) return fail("kgpu_bank_set_weights: channel not defined");
+  ChanAux &x = b->ch[(size_t)idx].aux;
+  x.are = alpha_re;
+  x.aim = alpha_im;
+  x.bre = beta_re;
+  x.bim = beta_im;
+  b->dirty = true;
+  return 0;
+}
+extern "C" int kgpu_bank_set_osc(kgpu_bank *b, int idx, int enable, double phase_cycles, double freq_cps, double rate_cps2,
+                                 double block_adj_cycles) {
+  if (bad_idx(b, idx) || !b->ch[(size_t)idx].defined) return fail("kgpu_bank_set_osc: channel not defined");
+  ChanHost &c = b->ch[(size_t)idx];
+  if (!std::isfinite(phase_cycles) || !std::isfinite(freq_cps) || !std::isfinite(rate_cps2) || !std::isfinite(block_adj_cycles))
+    return fail("kgpu_bank_set_osc: non-finite parameter");
+  c.flags = enable ? (c.flags | kChanOsc) : (c.flags & ~kChanOsc);
+  c.aux.osc_phase = phase_cycles - floor(phase_cycles);
+  c.aux.osc_freq = freq_cps;
+  c.aux.osc_rate = rate_cps2;
+  c.aux.osc_adj = block_adj_cycles;
+  c.aux.osc_epoch = b->block_counter;
+  b->dirty = true;
+  return 0;
+}
+extern "C" int kgpu_bank_get_osc_phase(kgpu_bank *b, int idx, double *phase_cycles) {
+  if (bad_idx(b, idx) || !b->ch[(size_t)idx].defined || !phase_cycles) return fail("kgpu_bank_get_osc_phase: bad arguments");
+  ChanHost const &c = b->ch[(size_t)idx];
+  long const K = b->block_counter - c.aux.osc_epoch;
+  double const D = (double)K * (double)c.olen;
+  double const ph = c.aux.osc_phase + (double)K * c.aux.osc_adj + D * c.aux.osc_freq + 0.5 * D * (D + 1.0) * c.aux.osc_rate;
+  *phase_cycles = ph - floor(ph);
+  return 0;
+}
+extern "C" int kgpu_bank_set_block_counter(kgpu_bank *b, long counter) {
+  if (!b) return fail("kgpu_bank_set_block_counter: bad arguments");
+  b->block_counter = counter;
+  return 0;
+}
+extern "C" long kgpu_bank_block_counter(kgpu_bank const *b) { return b ? b->block_counter : -1; }
 extern "C" int kgpu_bank_enable(kgpu_bank *b, int idx, int enabled) {
   if (bad_idx(b, idx) || !b->ch[(size_t)idx].defined) return fail("kgpu_bank_enable: channel not defined");
   if (b->ch[(size_t)idx].enabled != (enabled != 0)) {
@@ -1139,15 +1251,16 @@ extern "C" long kgpu_bank_out_offset(kgpu_bank const *b, int idx) {
   return idx < b->nchan ? b->out_off[(size_t)idx] : -1;
 }
 
-template <class P> static int launch_chan_v2(ChanArgs const &a, int n, int nblocks, cudaStream_t st) {
+template <class P> static int launch_chan_v2(ChanArgs const &a, int n, int nblocks, cudaStream_t st, bool osc) {
   size_t const sm = sizeof(float2) * ((size_t)(2 * P::len + 4) * kChanWarps + static_tw_count<P>() + 2);
   static bool attr_done = false;
   if (!attr_done) {
-    if (set_smem((const void *)chan_v2<P>, sm)) return -1;
+    if (set_smem((const void *)chan_v2<P, false>, sm) || set_smem((const void *)chan_v2<P, true>, sm)) return -1;
     attr_done = true;
   }
   dim3 const g((unsigned)((n + kChanWarps - 1) / kChanWarps), (unsigned)nblocks);
-  chan_v2<P><<<g, kChanWarps * 32, sm, st>>>(a);
+  if (osc) chan_v2<P, true><<<g, kChanWarps * 32, sm, st>>>(a);
+  else chan_v2<P, false><<<g, kChanWarps * 32, sm, st>>>(a);
   return 0;
 }
 
@@ -1178,7 +1291,8 @@ template <class P> static int launch_chan_static(ChanArgs const &a, int n, int n
 
 // one (plan, descriptor list) launch
 static int launch_chan(kgpu_bank *b, const void *d_spec, int nblocks, void *d_out, long out_stride, int plan,
-                       int points, int const *d_order, int base, int n, cudaStream_t st) {
+                       int points, int const *d_order, int base, int n, cudaStream_t st, bool generic = false,
+                       float *d_power = nullptr) {
   ChanArgs a;
   a.spec = (float2 const *)d_spec;
   a.spec_stride = b->m->spec_stride;
@@ -1192,18 +1306,22 @@ static int launch_chan(kgpu_bank *b, const void *d_spec, int nblocks, void *d_ou
   a.out = (float2 *)d_out;
   a.out_stride = out_stride;
   a.pitch = (points + 3) / 4 * 4 + 2;
+  a.aux = b->d_aux;
+  a.block0 = b->block_counter;
+  a.power = d_power;
+  a.power_stride = b->capacity;
   ProfScope ps(K_CHAN, st);
   g_launches++;
   TilePlan const *tp = host_tile_plan(plan);
-  if (g_static_on.load()) {
-    if (g_tuning[6].load() == 2 && !a.wrap) {  // lane-packed variant: REAL master, no ISB channel in the bank
+  if (g_static_on.load() && !generic) {
+    if (g_tuning[6].load() == 2 && !a.wrap && !b->any_osc) {  // lane-packed variant: REAL master, no ISB channel in the bank
       bool isb = false;
       for (int i = 0; i < b->nchan && !isb; i++) isb = b->ch[(size_t)i].defined && (b->ch[(size_t)i].flags & 1);
       if (!isb && plan_is<S600>(tp)) return launch_chan_v3<S600>(a, n, nblocks, st);
     }
     if (g_tuning[6].load() != 1) {
-      if (plan_is<S600>(tp)) return launch_chan_v2<S600>(a, n, nblocks, st);
-      if (plan_is<S300>(tp)) return launch_chan_v2<S300>(a, n, nblocks, st);
+      if (plan_is<S600>(tp)) return launch_chan_v2<S600>(a, n, nblocks, st, b->any_osc);
+      if (plan_is<S300>(tp)) return launch_chan_v2<S300>(a, n, nblocks, st, b->any_osc);
     }
     if (plan_is<S600>(tp)) return launch_chan_static<S600>(a, n, nblocks, st);
     if (plan_is<S300>(tp)) return launch_chan_static<S300>(a, n, nblocks, st);
@@ -1216,17 +1334,29 @@ static int launch_chan(kgpu_bank *b, const void *d_spec, int nblocks, void *d_ou
   return 0;
 }
 
-extern "C" int kgpu_bank_run(kgpu_bank *b, const void *d_spec, int nblocks, void *d_out, void *stream) {
-  if (!b || !d_spec || !d_out || nblocks < 1) return fail("kgpu_bank_run: bad arguments");
+extern "C" int kgpu_bank_run_ex(kgpu_bank *b, const void *d_spec, int nblocks, void *d_out, long out_pitch, float *d_power, void *stream) {
+  if (!b || !d_spec || !d_out || nblocks < 1 || out_pitch < 0) return fail("kgpu_bank_run: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
+  if (b->any_osc && b->block_counter - b->last_rebase > 4096) b->dirty = true;  // keep oscillator phases small
   if (bank_commit(b, st)) return -1;
+  if (out_pitch && out_pitch < b->out_stride) return fail("kgpu_bank_run_ex: out_pitch %ld < packed row %ld", out_pitch, b->out_stride);
   for (auto const &g : b->groups)
-    if (launch_chan(b, d_spec, nblocks, d_out, b->out_stride, g.plan, g.points, b->d_order + g.off, 0, g.count, st))
+    if (launch_chan(b, d_spec, nblocks, d_out, out_pitch ? out_pitch : b->out_stride, g.plan, g.points, b->d_order + g.off, 0, g.count,
+                    st, g.generic, d_power))
       return -1;
+  b->block_counter += nblocks;
   CUDA_OK(cudaGetLastError());
   return 0;
 }
+extern "C" int kgpu_bank_run(kgpu_bank *b, const void *d_spec, int nblocks, void *d_out, void *stream) {
+  return kgpu_bank_run_ex(b, d_spec, nblocks, d_out, 0, nullptr, stream);
+}
+extern "C" int kgpu_bank_run_one_ex(kgpu_bank *b, int idx, const void *d_spec, void *d_out, float *d_power, void *stream);
 extern "C" int kgpu_bank_run_one(kgpu_bank *b, int idx, const void *d_spec, void *d_out, void *stream) {
+  return kgpu_bank_run_one_ex(b, idx, d_spec, d_out, nullptr, stream);
+}
+// d_power: nullptr or one float; the block is taken to be block_counter (set it with kgpu_bank_set_block_counter)
+extern "C" int kgpu_bank_run_one_ex(kgpu_bank *b, int idx, const void *d_spec, void *d_out, float *d_power, void *stream) {
   if (bad_idx(b, idx) || !d_spec || !d_out) return fail("kgpu_bank_run_one: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   if (bank_commit(b, st)) return -1;
@@ -1234,7 +1364,36 @@ extern "C" int kgpu_bank_run_one(kgpu_bank *b, int idx, const void *d_spec, void
   if (!c.defined || !c.has_response || !c.enabled) return fail("kgpu_bank_run_one: channel %d not runnable", idx);
   // write this channel's olen samples at d_out[0..olen): shift the row origin back by out_off
   float2 *origin = (float2 *)d_out - b->out_off[(size_t)idx];
-  if (launch_chan(b, d_spec, 1, origin, 0, c.plan, c.points, nullptr, idx, 1, st)) return -1;
+  bool const gen = (b->desc[(size_t)idx].flags & (kChanRealOut | kChanBeam)) != 0;
+  if (launch_chan(b, d_spec, 1, origin, 0, c.plan, c.points, nullptr, idx, 1, st, gen, d_power ? d_power - idx : nullptr)) return -1;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+// Noise density per channel and block from the device-resident spectrum (estimate_noise, radio.c:1783-1866).
+extern "C" int kgpu_bank_noise(kgpu_bank *b, const void *d_spec, int nblocks, double samprate, double *d_n0, void *stream) {
+  if (!b || !d_spec || !d_n0 || nblocks < 1 || !(samprate > 0)) return fail("kgpu_bank_noise: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bank_commit(b, st)) return -1;
+  if (b->nchan == 0) return 0;
+  double const NQ = 0.10, N_cutoff = 1.5;  // radio.c:73-74
+  double const z = N_cutoff * (-log(1 - NQ));
+  double const correction = 1 / (1 - z * exp(-z) / (1 - exp(-z)));  // radio.c:1842-1843
+  NoiseArgs a;
+  a.spec = (float2 const *)d_spec;
+  a.spec_stride = b->m->spec_stride;
+  a.m_bins = b->m->bins;
+  a.wrap = (b->m->in_type == KGPU_COMPLEX);
+  a.desc = b->d_desc;
+  a.shift = b->d_shift;
+  a.nchan = b->nchan;
+  a.scale = correction / ((double)b->m->bins * samprate);
+  a.n0 = d_n0;
+  a.n0_stride = b->capacity;
+  {
+    ProfScope ps(K_NOISE, st);
+    noise_kernel<<<dim3((unsigned)b->nchan, (unsigned)nblocks), kNoiseThreads, 0, st>>>(a);
+  }
+  g_launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(kChanWarps * 32) chan_static(ChanArgs const a)
 
   if (d.ncopy <= 0) {  // nothing of this channel overlaps the master spectrum: zeros (filter.c:823-832)
     for (int i = lane; i < d.olen; i += 32) dst[i] = make_float2(0.f, 0.f);
+    if ((d.flags & kChanOsc) && a.power && lane == 0) a.power[(long)blk * a.power_stride + (a.order ? a.order[oi] : a.chan_base + oi)] = 0.f;
     mbar_wait(&tbar, 0);  // never retire the CTA with its twiddle copy still in flight
     return;
   }
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(kChanWarps * 32) chan_static(ChanArgs const a)
     col[wp] = live ? v : make_float2(0.f, 0.f);
   }
   __syncwarp();
-  if (d.flags & 1) {
+  if (d.flags & kChanIsb) {
     for (int p = 1 + lane; p < NS / 2; p += 32) {
       float2 const pos = col[p], neg = col[NS - p];
       col[p] = make_float2(pos.x + neg.x, pos.y - neg.y);
@@ -411,6 +412,20 @@ __global__ void __launch_bounds__(kChanWarps * 32) chan_static(ChanArgs const a)
   mbar_wait(&tbar, 0);
   StaticFft<P, true, true>::run(col, s_tw, lane);
   int const first = NS - d.olen;
+  if (d.flags & kChanOsc) {  // fine-tuning rotation + block power (radio.c:1476-1501, :1515-1520)
+    int const ci = a.order ? a.order[oi] : a.chan_base + oi;
+    ChanAux const ax = a.aux[ci];
+    long const k = a.block0 + blk - ax.osc_epoch;
+    float pw = 0.f;
+    for (int i = lane; i < d.olen; i += 32) {
+      float2 const v = osc_rotate(col[static_slot<P>(first + i)], osc_phase_cycles(ax, k, d.olen, i));
+      dst[i] = v;
+      pw += v.x * v.x + v.y * v.y;
+    }
+    pw = warp_sum(pw);
+    if (a.power && lane == 0) a.power[(long)blk * a.power_stride + ci] = pw / (float)d.olen;
+    return;
+  }
 #pragma unroll 4
   for (int i = lane; i < d.olen; i += 32) dst[i] = col[static_slot<P>(first + i)];
 }

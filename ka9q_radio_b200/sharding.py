@@ -37,12 +37,13 @@ class PipelinedSharder:
     broadcast: Callable[[int], object]
     channels: Callable[[int, int], None]
     depth: int = 2
+    forward_on_all: bool = False   # block-parallel forward: every rank transforms its share, the collective is an all-gather
 
     def run(self, steps: Sequence[int]) -> None:
         pending: list[tuple[int, int, object]] = []
         for i, step in enumerate(steps):
             slot = i % self.depth
-            if self.rank == 0:
+            if self.rank == 0 or self.forward_on_all:
                 self.forward(step, slot)
             handle = self.broadcast(slot) if self.world > 1 else None
             pending.append((step, slot, handle))

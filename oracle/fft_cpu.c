@@ -219,8 +219,10 @@ void kfft_c2r_f(kfft_plan const *half, float complex const *in, float *out) {
   int const h = half->n;
   float complex *z = (float complex *)kfft_scratch(KFFT_NSLOT - 1, sizeof(float complex) * (size_t)h);
   for (int k = 0; k < h; k++) {
-    float complex const a = in[k];
-    float complex const b = conjf(in[h - k]);
+    /* FFTW's c2r works on the halfcomplex representation, which has no slot for the imaginary parts of the DC and
+     * Nyquist bins: whatever the caller left there (the reference leaves X[shift] R[0], filter.c:803-809) is ignored */
+    float complex const a = (k == 0) ? (float complex)crealf(in[0]) : in[k];
+    float complex const b = (k == 0) ? (float complex)crealf(in[h]) : conjf(in[h - k]);
     float complex const e = a + b;
     float complex const o = a - b;
     float complex const wo = (float complex)conj(half->rtw[k]) * o;

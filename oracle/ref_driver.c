@@ -198,6 +198,8 @@ static void *chan_thread(void *p) {
   a->sink = acc;
   return NULL;
 }
+static double ref_bench_run(struct ref_session *s, int L, int in_type, int nchan, int const *shifts, void const *input, long nin,
+                            int nblocks, int nworkers, unsigned *drops_out);
 double ref_bench(int L, int M, int in_type, int nchan, int olen, int const *shifts, double low, double high,
                  double beta, void const *input, long nin, int nblocks, int nworkers, unsigned *drops_out) {
   struct ref_session *s = ref_open(L, M, in_type, nworkers);
@@ -206,6 +208,22 @@ double ref_bench(int L, int M, int in_type, int nchan, int olen, int const *shif
   for (int i = 0; i < nchan; i++)
     if (ref_add_channel(s, olen, COMPLEX, low, high, beta) < 0)
       return -1;
+  return ref_bench_run(s, L, in_type, nchan, shifts, input, nin, nblocks, nworkers, drops_out);
+}
+/* same with per-channel output lengths and filters (mixed-rate banks, BASELINE cfg-3) */
+double ref_bench_mixed(int L, int M, int in_type, int nchan, int const *olen, int const *shifts, double const *low,
+                       double const *high, double const *beta, void const *input, long nin, int nblocks, int nworkers,
+                       unsigned *drops_out) {
+  struct ref_session *s = ref_open(L, M, in_type, nworkers);
+  if (!s)
+    return -1;
+  for (int i = 0; i < nchan; i++)
+    if (ref_add_channel(s, olen[i], COMPLEX, low[i], high[i], beta[i]) < 0)
+      return -1;
+  return ref_bench_run(s, L, in_type, nchan, shifts, input, nin, nblocks, nworkers, drops_out);
+}
+static double ref_bench_run(struct ref_session *s, int L, int in_type, int nchan, int const *shifts, void const *input, long nin,
+                            int nblocks, int nworkers, unsigned *drops_out) {
   struct chan_arg *args = calloc((size_t)nchan, sizeof *args);
   pthread_t *tids = calloc((size_t)nchan, sizeof *tids);
   pthread_attr_t attr;

@@ -112,6 +112,83 @@ int ref_execute_channel(struct ref_session *s, int ch, int shift, float complex 
   return r;
 }
 unsigned ref_channel_drops(struct ref_session *s, int ch) { return s->out[ch]->block_drops; }
+int ref_set_beam(struct ref_session *s, int ch, int beam, double ire, double iim, double qre, double qim) {
+  s->out[ch]->beam = beam != 0;
+  return set_filter_weights(s->out[ch], ire + I * iim, qre + I * qim);
+}
+/* REAL-output slave (wfm.c:76-77,188): dst receives olen floats */
+int ref_execute_channel_real(struct ref_session *s, int ch, int shift, float *dst) {
+  struct filter_out *o = s->out[ch];
+  int const r = execute_filter_output(o, shift);
+  if (dst && o->output.r)
+    memcpy(dst, o->output.r, sizeof(float) * (size_t)o->olen);
+  return r;
+}
+/* the consumer falls `skip` blocks behind before it asks again: lap semantics of filter.c:690-701.
+ * Returns block_drops afterwards; dst receives what that execute_filter_output left in output.c */
+unsigned ref_lap_probe(struct ref_session *s, int ch, int shift, float const *x, int skip, float complex *dst) {
+  struct filter_out *o = s->out[ch];
+  int const L = s->in.ilen;
+  /* written from another thread context than the consumer: the producer must not be `owner` of this call's thread
+   * (filter.c:681-683 would hand it the latest block instead); ref_lap_producer below runs the writes */
+  (void)x;
+  (void)skip;
+  (void)L;
+  execute_filter_output(o, shift);
+  if (dst && o->output.c)
+    memcpy(dst, o->output.c, sizeof(float complex) * (size_t)o->olen);
+  return o->block_drops;
+}
+struct lap_arg {
+  struct ref_session *s;
+  float const *x;
+  int nblocks;
+};
+static void *lap_producer(void *p) {
+  struct lap_arg *a = p;
+  int const L = a->s->in.ilen;
+  for (int b = 0; b < a->nblocks; b++)
+    write_rfilter(&a->s->in, a->x + (size_t)b * L, L);
+  return NULL;
+}
+/* nblocks blocks written by a separate producer thread (joined before returning) */
+int ref_produce_from_thread(struct ref_session *s, float const *x, int nblocks) {
+  struct lap_arg a = {s, x, nblocks};
+  pthread_t t;
+  if (pthread_create(&t, NULL, lap_producer, &a) != 0)
+    return -1;
+  pthread_join(t, NULL);
+  return 0;
+}
+unsigned ref_channel_next_job(struct ref_session *s, int ch) { return s->out[ch]->next_jobnum; }
+#ifdef KA9Q_GPU_FILTER_H
+/* extensions of the GPU library */
+int ref_execute_tuned(struct ref_session *s, int ch, int shift, double remainder, double samprate, double doppler_rate,
+                      float complex *dst, double *bb_power) {
+  struct filter_out *o = s->out[ch];
+  int const r = execute_filter_output_tuned(o, shift, remainder, samprate, doppler_rate, bb_power);
+  if (dst && o->output.c)
+    memcpy(dst, o->output.c, sizeof(float complex) * (size_t)o->olen);
+  return r;
+}
+int ref_enable_noise(struct ref_session *s, double samprate) { return filter_input_enable_noise(&s->in, samprate); }
+double ref_noise(struct ref_session *s, int ch) { return filter_noise_estimate(s->out[ch]); }
+/* all channels of the session with one call; dst: nchan pointers to olen complex each */
+int ref_execute_batch(struct ref_session *s, int const *shifts, float complex **dst) {
+  int const r = execute_filter_output_batch((struct filter_out *const *)s->out, shifts, s->nchan);
+  for (int i = 0; i < s->nchan; i++)
+    if (dst && dst[i] && s->out[i]->output.c)
+      memcpy(dst[i], s->out[i]->output.c, sizeof(float complex) * (size_t)s->out[i]->olen);
+  return r;
+}
+int ref_write_i16_inplace(struct ref_session *s, int16_t const *x, int n, float scale) {
+  int16_t *w = filter_i16_write_pointer(&s->in);
+  if (!w)
+    return -1;
+  memcpy(w, x, sizeof(int16_t) * (size_t)n);
+  return write_i16filter(&s->in, NULL, n, scale, false);
+}
+#endif
 unsigned long long ref_channel_sample_index(struct ref_session *s, int ch) { return s->out[ch]->sample_index; }
 void ref_close(struct ref_session *s) {
   if (!s)

@@ -1,0 +1,218 @@
+"""GPU parity of the slice variants and per-channel steps added in round 2, each against the oracle restatement that
+tests/test_oracle_ext_cpu.py pins to the reference's own filter.c / radio.c:
+  REAL-output slaves (filter.c:794-809 + c2r), beam synthesis (filter.c:756-775),
+  fine-tuning oscillator + block phase + baseband power (radio.c:1476-1501, :1515-1520),
+  noise-density estimate from the device spectrum (radio.c:1783-1866).
+Tolerance: north_star's 1e-5 relative (max|gpu - ref| / max|ref| per channel-block)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _mk(L, M, in_type, dev, cap=64):
+    from ka9q_radio_b200.channelizer import Channelizer
+
+    return Channelizer(L, M, in_type, dev, capacity=cap)
+
+
+def _stream(oracle, in_type, n, f=0.0123):
+    from ka9q_radio_b200 import capi
+
+    return oracle.siggen_real(n, 0.1, 0.02, f, 1.0) if in_type == capi.KGPU_REAL else oracle.siggen_complex(n, 0.1, 0.02, f, 1.0)
+
+
+@pytest.mark.parametrize("master", ["real", "complex"])
+def test_real_output_slaves(oracle, cuda_dev, master):
+    from ka9q_radio_b200 import capi
+
+    it = capi.KGPU_REAL if master == "real" else capi.KGPU_COMPLEX
+    L, M, nb = 4800, 1201, 3
+    N = L + M - 1
+    x = _stream(oracle, it, nb * L)
+    # (olen, low, high, beta, shift): wfm.c:76-77 / stereod.c:387-389 use shift 0; other shifts exercise the index math
+    cases = [(480, 50 / 24000, 0.3, 11.0, 0), (960, 0.01, 0.45, 7.0, 0), (480, -0.2, 0.25, 11.0, 40), (240, 0.05, 0.3, 5.0, -7),
+             (480, 0.1, 0.4, 11.0, 2900), (480, 0.1, 0.4, 11.0, -2900), (96, 0.0, 0.5, 3.0, 5)]
+    cz = _mk(L, M, it, cuda_dev, cap=len(cases) + 2)
+    for c in cases:
+        cz.add_channel(c[0], c[4], c[1], c[2], c[3], out_type=capi.KGPU_REAL)
+    cz.add_channel(480, 77, -0.3, 0.3, 11.0)  # a COMPLEX slave in the same bank: mixed groups in one run
+    spec, out = cz.alloc_spectra(nb), cz.alloc_outputs(nb)
+    cz.forward(cz.stage_stream(x), nb, spec)
+    cz.channels(spec, nb, out)
+    torch.cuda.synchronize()
+    for b in range(nb):
+        X = oracle.forward(oracle.block_window(x, L, M, b))
+        for i, c in enumerate(cases):
+            pts = c[0] * N // L
+            R = oracle.design_response_realout(pts, c[0], N, it == capi.KGPU_REAL, c[1], c[2], c[3])
+            ref = oracle.channel_block_realout(it, X, R, c[4])[-c[0]:]
+            got = cz.channel_slice(out, i).cpu().numpy()[b]
+            assert got.dtype == np.float32 and got.shape == ref.shape
+            den = max(np.abs(ref).max(), 1e-9)
+            assert np.abs(got - ref).max() / den < TOL, (b, c)
+        Rc = oracle.design_response(600, 480, N, it == capi.KGPU_REAL, -0.3, 0.3, 11.0)
+        refc = oracle.channel_block(it, X, Rc, 77)[-480:]
+        assert rel_err(cz.channel_slice(out, len(cases)).cpu().numpy()[b], refc) < TOL
+    cz.close()
+
+
+def test_beam_synthesis(oracle, cuda_dev):
+    from ka9q_radio_b200 import capi
+
+    L, M, nb = 4000, 1001, 3
+    N = L + M - 1
+    x = _stream(oracle, capi.KGPU_COMPLEX, nb * L)
+    cases = [(480, 615, 1.0, 0.0), (480, -615, 0.0, 1.0), (160, 300, 0.6 - 0.2j, 0.3 + 0.7j), (80, 0, 1.0, 1j), (480, 2100, 0.5, -0.5j),
+             (480, -2150, 0.2j, 0.9), (480, 1, 1.0, 1.0)]
+    cz = _mk(L, M, capi.KGPU_COMPLEX, cuda_dev, cap=len(cases))
+    for c in cases:
+        cz.add_channel(c[0], c[1], -0.3, 0.35, 11.0, beam=(c[2], c[3]))
+    spec, out = cz.alloc_spectra(nb), cz.alloc_outputs(nb)
+    cz.forward(cz.stage_stream(x), nb, spec)
+    cz.channels(spec, nb, out)
+    torch.cuda.synchronize()
+    for b in range(nb):
+        X = oracle.forward(oracle.block_window(x, L, M, b))
+        for i, c in enumerate(cases):
+            pts = c[0] * N // L
+            R = oracle.design_response(pts, c[0], N, False, -0.3, 0.35, 11.0)
+            ref = oracle.channel_block_beam(X, R, c[1], c[2], c[3])[-c[0]:]
+            assert rel_err(cz.channel_slice(out, i).cpu().numpy()[b], ref) < TOL, (b, c)
+    cz.close()
+
+
+@pytest.mark.parametrize("static", [1, 0])
+@pytest.mark.parametrize("master", ["real", "complex"])
+def test_fine_tuning_oscillator_and_power(oracle, cuda_dev, master, static):
+    """radio.c:1476-1520 fused into the channel kernels: per-sample rotation, per-block phase step, the one-time term
+    on a shift change, set_osc on a remainder change, baseband power -- across launches of 1..3 blocks, for the
+    600 / 300 / 1200-point kernels and an ISB channel (the unfused path)."""
+    from ka9q_radio_b200 import capi
+
+    capi.load().kgpu_use_static_kernels(static)
+    it = capi.KGPU_REAL if master == "real" else capi.KGPU_COMPLEX
+    L, M, fs = (48000, 12001, 2.4e6) if it == capi.KGPU_REAL else (40000, 10001, 2.0e6)
+    N = L + M - 1
+    # (olen, out rate, low, high, beta, isb)
+    chans = [(480, 24000.0, -1 / 3, 1 / 3, 11.0, False), (240, 12000.0, 50 / 12000, 3000 / 12000, 11.0, False),
+             (960, 48000.0, -0.4, 0.4, 7.0, False), (480, 24000.0, -0.2, 0.2, 5.0, True), (160, 8000.0, -0.3, 0.3, 9.0, False)]
+    nb = 9
+    base = [300_017.3, 412_234.5, 600_000.0, 250_123.4, 99_999.9]
+    if it == capi.KGPU_COMPLEX:
+        base = [f - 350_000.0 for f in base]  # both signs
+    plan = [list(base) for _ in range(nb)]
+    for b in range(4, nb):
+        plan[b][0] = base[0] + 3_333.3          # new shift (not a multiple of V) and remainder
+    for b in range(6, nb):
+        plan[b][1] = base[1] + 7.25             # same shift, new remainder
+    for b in range(7, nb):
+        plan[b][2] = base[2] - 40_000.0
+    x = _stream(oracle, it, nb * L, 0.1234)
+    cz = _mk(L, M, it, cuda_dev, cap=len(chans))
+    resp = []
+    for c in chans:
+        cz.add_channel(c[0], 0, c[2], c[3], c[4], isb=c[5])
+        resp.append(oracle.design_response(c[0] * N // L, c[0], N, it == capi.KGPU_REAL, c[2], c[3], c[4]))
+    fts = [oracle.FineTune(L, M, c[1]) for c in chans]
+    d = cz.stage_stream(x)
+    worst_y, worst_p = 0.0, 0.0
+    b0 = 0
+    for nblk in (1, 3, 2, 1, 2):  # launches of different sizes; retunes happen at launch boundaries (as in radiod: per block)
+        tun = []
+        for i, c in enumerate(chans):
+            rc, shift, rem = oracle.compute_tuning(N, fs, plan[b0][i])
+            assert rc == 0 and all(plan[b0 + k][i] == plan[b0][i] for k in range(nblk))
+            cz.tune(i, shift, rem, c[1])
+            tun.append((shift, rem))
+        spec, out, pw = cz.alloc_spectra(nblk), cz.alloc_outputs(nblk), cz.alloc_power(nblk)
+        cz.forward(d, nblk, spec, first_block=b0)
+        cz.channels(spec, nblk, out, pw)
+        torch.cuda.synchronize()
+        pwh = pw.cpu().numpy()
+        for k in range(nblk):
+            X = oracle.forward(oracle.block_window(x, L, M, b0 + k))
+            for i, c in enumerate(chans):
+                y = oracle.channel_block(it, X, resp[i], tun[i][0], c[5])[-c[0]:].copy()
+                p_ref = fts[i].block(y, tun[i][0], tun[i][1])
+                got = cz.channel_slice(out, i).cpu().numpy()[k]
+                worst_y = max(worst_y, rel_err(got, y))
+                worst_p = max(worst_p, abs(pwh[k, i] - p_ref) / p_ref)
+        b0 += nblk
+    assert b0 == nb
+    cz.close()
+    capi.load().kgpu_use_static_kernels(1)
+    assert worst_y < TOL and worst_p < TOL, (worst_y, worst_p)
+
+
+def test_oscillator_doppler_rate_and_long_run(oracle, cuda_dev):
+    """non-zero sweep rate (phasor_step_step, osc.c:64-66) and 6000 blocks between retunes (the host re-bases the
+    epoch every 4096 blocks): the closed-form device phase stays on the reference's recursive oscillator."""
+    from ka9q_radio_b200 import capi
+
+    L, M, fs = 480, 121, 24000.0
+    N = L + M - 1
+    cz = _mk(L, M, capi.KGPU_COMPLEX, cuda_dev, cap=2)
+    ident = np.zeros(60, np.complex64)
+    ident[:] = 1.0 / 60  # flat response: output = scaled input slice, content irrelevant here
+    for i in range(2):
+        cz.add_channel(48, 37, response=ident)
+    rate_hz_s = 35.0
+    cz.tune(0, 37, 3.21, 2400.0, doppler_rate=rate_hz_s)
+    cz.tune(1, 37, -11.5, 2400.0)
+    fts = [oracle.FineTune(L, M, 2400.0) for _ in range(2)]
+    rng = np.random.default_rng(2)
+    X = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64)
+    spec = cz.alloc_spectra(1)
+    spec[0, :N] = torch.from_numpy(X).to(cuda_dev)
+    y0 = oracle.channel_block(capi.KGPU_COMPLEX, X, ident, 37)[-48:]
+    out, pw = cz.alloc_outputs(1), cz.alloc_power(1)
+    worst = 0.0
+    for b in range(6000):
+        cz.channels(spec, 1, out, pw)
+        refs = []
+        for i, dr in ((0, rate_hz_s), (1, 0.0)):
+            y = y0.copy()
+            fts[i].block(y, 37, 3.21 if i == 0 else -11.5, dr)
+            refs.append(y)
+        if b % 500 == 499 or b in (0, 1, 4095, 4096, 4097):
+            torch.cuda.synchronize()
+            for i in range(2):
+                worst = max(worst, rel_err(cz.channel_slice(out, i).cpu().numpy()[0], refs[i]))
+    cz.close()
+    assert worst < TOL, worst
+
+
+@pytest.mark.parametrize("master", ["real", "complex"])
+def test_noise_estimate_on_device(oracle, cuda_dev, master):
+    from ka9q_radio_b200 import capi
+
+    it = capi.KGPU_REAL if master == "real" else capi.KGPU_COMPLEX
+    L, M, fs, nb = 48000, 12001, 2.4e6, 3
+    N = L + M - 1
+    x = _stream(oracle, it, nb * L, 0.21)
+    if it == capi.KGPU_REAL:
+        shifts = [7380, -7380, 0, 3, 29990, -29500, 250, 15000, 480]
+        olens = [480, 240, 960, 480, 480, 960, 160, 1600, 480]
+    else:
+        shifts = [7380, -7380, 0, 3, 29000, -29000, -250, 15000, -12345]
+        olens = [480, 240, 960, 480, 480, 960, 160, 1600, 480]
+    cz = _mk(L, M, it, cuda_dev, cap=len(shifts))
+    for s, o in zip(shifts, olens):
+        cz.add_channel(o, s, -0.3, 0.3, 11.0)
+    spec = cz.alloc_spectra(nb)
+    cz.forward(cz.stage_stream(x), nb, spec)
+    n0 = cz.noise(spec, nb, fs)
+    torch.cuda.synchronize()
+    got = n0.cpu().numpy()
+    sp = spec.cpu().numpy()
+    for b in range(nb):
+        X = np.ascontiguousarray(sp[b, : cz.master.bins])  # the estimator's input IS the device spectrum
+        for i, (s, o) in enumerate(zip(shifts, olens)):
+            ref = oracle.estimate_noise(it, X, o * N // L, s, fs)
+            assert ref > 0 and abs(got[b, i] - ref) / ref < 1e-6, (b, i, got[b, i], ref)
+    cz.close()
