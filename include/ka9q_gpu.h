@@ -77,6 +77,12 @@ int kgpu_master_describe(kgpu_master const *m, char *buf, int buflen);
 int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float scale, int derandomize, int nblocks,
                  void *d_spec, void *d_stats, void *stream);
 
+/* Airspy R2 / HydraSDR packed 12-bit ingest (replaces airspy_unpack / airspy_unpack_avx2, airspy-unpack.c:17-130, called at
+ * airspy.c:416-419): `sampcount` (multiple of 8) offset-binary samples, 8 per three 32-bit words, -> int16 (s - 2048) at
+ * d_i16 (16-byte aligned), ready for kgpu_forward(..., KGPU_FMT_I16, scale, ...) which applies `scale * (float)x`.
+ * d_stats: NULL or ONE kgpu_ingest_stats receiving the energy and the clip count (x == 2047 || x <= -2047). */
+int kgpu_unpack_airspy12(const void *d_packed, long sampcount, void *d_i16, void *d_stats, void *stream);
+
 /* Notch EWMA on listed bins (apply_notch_filters, filter.c:464-474); list ends with bin 0. The state
  * lives in the master; blocks are processed in order. */
 int kgpu_master_set_notches(kgpu_master *m, int const *bins, double const *alpha, int n);
@@ -135,6 +141,13 @@ int kgpu_bank_run_one_ex(kgpu_bank *b, int idx, const void *d_spec, void *d_out,
  * quantile :1722-1775) with the shift each channel was last given: d_n0[block*capacity + idx], doubles, in the
  * reference's scaling (energy per bin / (bins * samprate)).  Saves the 13 MB/block spectrum read-back. */
 int kgpu_bank_noise(kgpu_bank *b, const void *d_spec, int nblocks, double samprate, double *d_n0, void *stream);
+
+/* FM discriminator front half on the outputs a kgpu_bank_run* just produced (replaces the per-sample loops of demod_fm,
+ * fm.c:104-131 amplitude statistics and fm.c:205-231 plain quadrature discriminator): for every COMPLEX channel and block
+ *   d_baseband[block * 2*out_pitch + 2*out_offset(idx) + n] = arg(y[n] conj y[n-1]) / pi     (olen floats, y[-1] carried across calls)
+ *   d_stats[(block * capacity + idx) * 2 + {0,1}]           = mean |y|, sum (|y| - mean)^2   (doubles)
+ * out_pitch as given to kgpu_bank_run_ex (0 = packed). */
+int kgpu_bank_fm_front(kgpu_bank *b, const void *d_out, long out_pitch, int nblocks, float *d_baseband, double *d_stats, void *stream);
 
 /* Push pending channel changes (shift/filter/enable) to the device now, ordered after `stream`. */
 int kgpu_bank_commit(kgpu_bank *b, void *stream);

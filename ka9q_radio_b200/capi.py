@@ -75,6 +75,7 @@ def load() -> C.CDLL:
     L.kgpu_bank_run.argtypes = [vp, vp, i, vp, vp]
     L.kgpu_bank_run_one.argtypes = [vp, i, vp, vp, vp]
     L.kgpu_bank_commit.argtypes = [vp, vp]
+    L.kgpu_unpack_airspy12.argtypes = [vp, l, vp, vp, vp]
     L.kgpu_bank_define_ex.argtypes = [vp, i, i, i]
     L.kgpu_bank_set_weights.argtypes = [vp, i, d, d, d, d]
     L.kgpu_bank_set_osc.argtypes = [vp, i, i, d, d, d, d]
@@ -85,6 +86,7 @@ def load() -> C.CDLL:
     L.kgpu_bank_run_ex.argtypes = [vp, vp, i, vp, l, vp, vp]
     L.kgpu_bank_run_one_ex.argtypes = [vp, i, vp, vp, vp, vp]
     L.kgpu_bank_noise.argtypes = [vp, vp, i, d, vp, vp]
+    L.kgpu_bank_fm_front.argtypes = [vp, vp, l, i, vp, vp, vp]
     L.kgpu_use_static_kernels.argtypes = [i]
     L.kgpu_set_tuning.argtypes = [i, i]
     L.kgpu_set_debug_buffer.argtypes = [vp]
@@ -217,6 +219,9 @@ class Bank:
     @block_counter.setter
     def block_counter(self, v: int):
         check(self.lib.kgpu_bank_set_block_counter(self.h, int(v)), "kgpu_bank_set_block_counter")
+
+    def fm_front(self, d_out: int, nblocks: int, d_baseband: int, d_stats: int, stream: int = 0):
+        check(self.lib.kgpu_bank_fm_front(self.h, d_out, 0, nblocks, d_baseband, d_stats, stream or None), "kgpu_bank_fm_front")
 
     def noise(self, d_spec: int, nblocks: int, samprate: float, d_n0: int, stream: int = 0):
         check(self.lib.kgpu_bank_noise(self.h, d_spec, nblocks, samprate, d_n0, stream or None), "kgpu_bank_noise")

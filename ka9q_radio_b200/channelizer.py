@@ -127,6 +127,16 @@ class Channelizer:
         self.bank.noise(spectra.data_ptr(), nblocks, samprate, n0.data_ptr(), st)
         return n0
 
+    def fm_front(self, outputs: torch.Tensor, nblocks: int):
+        """FM discriminator front half (fm.c:104-131, :205-231) on the outputs channels() just wrote:
+        -> (baseband float32 [nblocks, 2*row], stats float64 [nblocks, capacity, 2] = mean |y|, sum of squared deviations);
+        channel idx's baseband samples are baseband[:, 2*out_offset(idx) : 2*out_offset(idx) + olen]."""
+        bb = torch.zeros((nblocks, 2 * outputs.shape[1]), dtype=torch.float32, device=self.device)
+        stats = torch.zeros((nblocks, self.capacity, 2), dtype=torch.float64, device=self.device)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        self.bank.fm_front(outputs.data_ptr(), nblocks, bb.data_ptr(), stats.data_ptr(), st)
+        return bb, stats
+
     def channel_slice(self, outputs: torch.Tensor, idx: int) -> torch.Tensor:
         off = self.bank.out_offset(idx)
         olen = self._olen[idx][0]

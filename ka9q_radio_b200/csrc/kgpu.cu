@@ -20,7 +20,7 @@
 #include "plan.cuh"
 #include "static_kernels.cuh"
 #include "static_kernels_v2.cuh"
-#include "static_kernels_v3.cuh"
+#include "fwd_cols_r36.cuh"
 
 using namespace kfft;
 
@@ -203,6 +203,57 @@ extern "C" int kgpu_multicast_copy(const void *d_src, void *mc_dst, unsigned lon
   return 0;
 }
 
+// ---- Airspy R2 / HydraSDR packed 12-bit ingest (airspy-unpack.c:17-130) ------------------------------------------
+// 8 offset-binary 12-bit samples in three 32-bit words -> 8 int16 (s - 2048), which the forward transform's fused
+// int16 ingest then scales exactly as the reference's `scale * (float)x`.  One thread per group: 12 contiguous bytes in,
+// one 16-byte store out.  Energy and clip count (x == 2047 || x <= -2047) as the reference returns them.
+__global__ void __launch_bounds__(256) airspy_unpack_kernel(uint32_t const *__restrict__ up, long ngroups, uint4 *__restrict__ out,
+                                                            IngestStats *stats) {
+  long const g = (long)blockIdx.x * 256 + threadIdx.x;
+  unsigned long long energy = 0;
+  unsigned int clips = 0;
+  if (g < ngroups) {
+    uint32_t const w0 = __ldg(up + 3 * g), w1 = __ldg(up + 3 * g + 1), w2 = __ldg(up + 3 * g + 2);
+    uint32_t s[8] = {w0 >> 20, w0 >> 8, (w0 << 4) | (w1 >> 28), w1 >> 16, w1 >> 4, (w1 << 8) | (w2 >> 24), w2 >> 12, w2};
+    int x[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      x[j] = (int)(s[j] & 0xfffu) - 2048;
+      clips += (x[j] == 2047 || x[j] <= -2047);
+      energy += (unsigned long long)(x[j] * x[j]);
+    }
+    uint4 o;
+    o.x = (uint32_t)(x[0] & 0xffff) | ((uint32_t)x[1] << 16);
+    o.y = (uint32_t)(x[2] & 0xffff) | ((uint32_t)x[3] << 16);
+    o.z = (uint32_t)(x[4] & 0xffff) | ((uint32_t)x[5] << 16);
+    o.w = (uint32_t)(x[6] & 0xffff) | ((uint32_t)x[7] << 16);
+    out[g] = o;
+  }
+  if (stats) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      energy += __shfl_xor_sync(0xffffffffu, energy, o);
+      clips += __shfl_xor_sync(0xffffffffu, clips, o);
+    }
+    if ((threadIdx.x & 31) == 0 && (energy | clips)) {
+      atomicAdd(&stats->energy, energy);
+      atomicAdd(&stats->clips, clips);
+    }
+  }
+}
+extern "C" int kgpu_unpack_airspy12(const void *d_packed, long sampcount, void *d_i16, void *d_stats, void *stream) {
+  if (!d_packed || !d_i16 || sampcount < 0 || (sampcount & 7)) return fail("kgpu_unpack_airspy12: sample count must be a multiple of 8");
+  if (((uintptr_t)d_i16 & 15) || ((uintptr_t)d_packed & 3)) return fail("kgpu_unpack_airspy12: output must be 16-byte aligned");
+  if (sampcount == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d_stats) CUDA_OK(cudaMemsetAsync(d_stats, 0, sizeof(IngestStats), st));
+  long const ng = sampcount / 8;
+  airspy_unpack_kernel<<<(unsigned)((ng + 255) / 256), 256, 0, st>>>((uint32_t const *)d_packed, ng, (uint4 *)d_i16, (IngestStats *)d_stats);
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int kgpu_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -273,7 +324,6 @@ int get_tile_plan(int len) {
   if (len > 1) {
     rad = choose_radices(len);
     if (rad.empty()) return -1;
-    if (len == 1296 && getenv("KGPU_R36")) rad = {36, 36};  // experiment, see S1296b
   }
   TilePlan p;
   memset(&p, 0, sizeof p);
@@ -356,10 +406,9 @@ struct kgpu_master {
   RowItem *d_items = nullptr;
   int n_item_ctas = 0;
   float2 *d_rootD = nullptr;
-  float2 *d_twA = nullptr, *d_twB = nullptr, *d_rootC = nullptr;  // static-kernel tables
-  float2 *d_twA64 = nullptr, *d_twB64 = nullptr;                  // same for 64 rows per step
+  float2 *d_rootC = nullptr;                                      // split roots of the row pass
   float2 *d_twU = nullptr, *d_twT = nullptr;                      // v2 cols kernel (1296 columns)
-  int nit = 0, nit64 = 0;
+  float2 *d_r36_tw0 = nullptr, *d_r36_A = nullptr, *d_r36_B = nullptr;  // 36 x 36 cols kernel
   int static_cols = 0, static_rows = 0;  // which specialised kernels apply (0 = generic)
   float2 *d_mid = nullptr;
   int mid_blocks = 0;
@@ -447,26 +496,14 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
   {
     TilePlan const *p1 = host_tile_plan(m->plan1), *p2 = host_tile_plan(m->plan2);
     if (plan_is<S1296>(p1)) m->static_cols = 1296;
-    if (plan_is<S1296b>(p1)) m->static_cols = 12960;
     if (plan_is<S1250>(p2)) m->static_rows = 1250;
     int const n2 = m->sp.n2;
-    m->nit = (n1 + 31) / 32;
-    std::vector<float2> tA((size_t)(n2 + 8) * m->nit, make_float2(0.f, 0.f)), tB((size_t)n2 * 32), tC((size_t)n1 / 2 + 1);
+    std::vector<float2> tC((size_t)n1 / 2 + 1);
     auto root = [](long e, long n) {
       long double const ang = -2.0L * M_PIl * (long double)(e % n) / (long double)n;
       return make_float2((float)cosl(ang), (float)sinl(ang));
     };
-    for (long c = 0; c < n2; c++) {
-      for (int it = 0; it < m->nit; it++) tA[(size_t)c * m->nit + it] = root(c * 32 * it, m->nc);
-      for (int r = 0; r < 32; r++) tB[(size_t)c * 32 + r] = root(c * r, m->nc);
-    }
     for (int k1 = 0; k1 <= n1 / 2; k1++) tC[(size_t)k1] = root(k1, 2 * m->nc);
-    m->nit64 = (n1 + 63) / 64;
-    std::vector<float2> tA64((size_t)(n2 + 8) * m->nit64, make_float2(0.f, 0.f)), tB64((size_t)n2 * 64);
-    for (long c = 0; c < n2; c++) {
-      for (int it = 0; it < m->nit64; it++) tA64[(size_t)c * m->nit64 + it] = root(c * 64 * it, m->nc);
-      for (int r = 0; r < 64; r++) tB64[(size_t)c * 64 + r] = root(c * r, m->nc);
-    }
     if (m->static_cols == 1296) {  // inter-pass factors in the v2 kernel's (u, t2) split
       std::vector<float2> tU((size_t)(n2 + 8) * 144, make_float2(0.f, 0.f)), tT((size_t)(n2 + 16) * 9 + 32, make_float2(0.f, 0.f));
       for (long c = 0; c < n2; c++) {
@@ -477,23 +514,25 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
       CUDA_OKP(cudaMalloc(&m->d_twT, sizeof(float2) * tT.size()));
       CUDA_OKP(cudaMemcpy(m->d_twU, tU.data(), sizeof(float2) * tU.size(), cudaMemcpyHostToDevice));
       CUDA_OKP(cudaMemcpy(m->d_twT, tT.data(), sizeof(float2) * tT.size(), cudaMemcpyHostToDevice));
+      // 36 x 36 variant: stage-0 powers, inter-pass factors A[n2][t] and the ten powers of W_nc^{36 n2}
+      static int const kPow[10] = {1, 2, 3, 4, 5, 6, 12, 18, 24, 30};
+      std::vector<float2> t0(360), tA36((size_t)n2 * 36), tB10((size_t)(n2 + 8) * 10, make_float2(0.f, 0.f));
+      for (int e = 0; e < 10; e++)
+        for (int j = 0; j < 36; j++) t0[(size_t)e * 36 + j] = root((long)j * kPow[e], 1296);
+      for (long c = 0; c < n2; c++) {
+        for (int t = 0; t < 36; t++) tA36[(size_t)c * 36 + t] = root(c * t, m->nc);
+        for (int e = 0; e < 10; e++) tB10[(size_t)c * 10 + e] = root(c * 36 * kPow[e], m->nc);
+      }
+      CUDA_OKP(cudaMalloc(&m->d_r36_tw0, sizeof(float2) * t0.size()));
+      CUDA_OKP(cudaMalloc(&m->d_r36_A, sizeof(float2) * tA36.size()));
+      CUDA_OKP(cudaMalloc(&m->d_r36_B, sizeof(float2) * tB10.size()));
+      CUDA_OKP(cudaMemcpy(m->d_r36_tw0, t0.data(), sizeof(float2) * t0.size(), cudaMemcpyHostToDevice));
+      CUDA_OKP(cudaMemcpy(m->d_r36_A, tA36.data(), sizeof(float2) * tA36.size(), cudaMemcpyHostToDevice));
+      CUDA_OKP(cudaMemcpy(m->d_r36_B, tB10.data(), sizeof(float2) * tB10.size(), cudaMemcpyHostToDevice));
     }
-    CUDA_OKP(cudaMalloc(&m->d_twA64, sizeof(float2) * tA64.size()));
-    CUDA_OKP(cudaMalloc(&m->d_twB64, sizeof(float2) * tB64.size()));
-    CUDA_OKP(cudaMemcpy(m->d_twA64, tA64.data(), sizeof(float2) * tA64.size(), cudaMemcpyHostToDevice));
-    CUDA_OKP(cudaMemcpy(m->d_twB64, tB64.data(), sizeof(float2) * tB64.size(), cudaMemcpyHostToDevice));
-    CUDA_OKP(cudaMalloc(&m->d_twA, sizeof(float2) * tA.size()));
-    CUDA_OKP(cudaMalloc(&m->d_twB, sizeof(float2) * tB.size()));
     CUDA_OKP(cudaMalloc(&m->d_rootC, sizeof(float2) * tC.size()));
-    CUDA_OKP(cudaMemcpy(m->d_twA, tA.data(), sizeof(float2) * tA.size(), cudaMemcpyHostToDevice));
-    CUDA_OKP(cudaMemcpy(m->d_twB, tB.data(), sizeof(float2) * tB.size(), cudaMemcpyHostToDevice));
     CUDA_OKP(cudaMemcpy(m->d_rootC, tC.data(), sizeof(float2) * tC.size(), cudaMemcpyHostToDevice));
-    size_t const s18 = sizeof(float2) * ((size_t)8 * 1328 + static_tw_count<S1296>() + 8 * 64),
-                 s14 = sizeof(float2) * ((size_t)4 * m->pitch1 + static_tw_count<S1296>()),
-                 s2 = sizeof(float2) * ((size_t)kTile * m->pitch2 + static_tw_count<S1250>());
-    (void)s14;
     size_t const sv1 = sizeof(float2) * (8 * 1298 + 1288 + 80), sv2 = sizeof(float2) * (8 * 1250 + 1246);
-    size_t const sv3 = sizeof(float2) * (2 * 8 * 1250 + 1246);
     if (set_smem((const void *)fwd_cols_v2<0>, sv1) || set_smem((const void *)fwd_cols_v2<1>, sv1) ||
         set_smem((const void *)fwd_cols_v2<2>, sv1) || set_smem((const void *)fwd_rows_v2<true>, sv2) ||
         set_smem((const void *)fwd_rows_v2<false>, sv2) ||
@@ -504,18 +543,10 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
         set_smem((const void *)fwd_cols_v2<2, 1250, 0, true>, sv1 + 128) ||
         set_smem((const void *)fwd_cols_v2<1, 1250, 0, false, 16>, sizeof(float2) * (16 * 1297 + 1288 + 160)) ||
         set_smem((const void *)fwd_cols_v2<1, 1250, 0, false, 6>, sizeof(float2) * (6 * 1298 + 1288 + 60)) ||
-        set_smem((const void *)fwd_cols_v3<1, 1250>, sv1) || set_smem((const void *)fwd_cols_v3<2, 1250>, sv1) ||
-        set_smem((const void *)fwd_rows_v3<true, 1296, true>, sv3) || set_smem((const void *)fwd_rows_v3<false, 1296, false>, sv3) ||
-        set_smem((const void *)fwd_rows_v3<true, 0, false>, sv3) || set_smem((const void *)fwd_rows_v3<false, 0, false>, sv3) || set_smem((const void *)fwd_rows_v2<false, 1296, false>, sv2) ||
-        set_smem((const void *)fwd_cols_static<0, S1296, 8, 1>, s18) || set_smem((const void *)fwd_cols_static<1, S1296, 8, 1>, s18) ||
-        set_smem((const void *)fwd_cols_static<2, S1296, 8, 1>, s18) || set_smem((const void *)fwd_cols_static<0, S1296, 8, 2>, s18) ||
-        set_smem((const void *)fwd_cols_static<1, S1296, 8, 2>, s18) || set_smem((const void *)fwd_cols_static<2, S1296, 8, 2>, s18) ||
-        set_smem((const void *)fwd_cols_static<1, S1296, 8, 2, 1>, s18) ||
-        set_smem((const void *)fwd_cols_static<1, S1296, 8, 2, 1, 2, true>, s18) ||
-        set_smem((const void *)fwd_rows_static<S1250, true, 2, true>, s2) ||
-        set_smem((const void *)fwd_cols_static<1, S1296b, 8, 1, 0, 2>, s18) ||
-        set_smem((const void *)fwd_rows_static<S1250, true, 1>, s2) || set_smem((const void *)fwd_rows_static<S1250, false, 1>, s2) ||
-        set_smem((const void *)fwd_rows_static<S1250, true, 2>, s2) || set_smem((const void *)fwd_rows_static<S1250, false, 2>, s2)) {
+        set_smem((const void *)fwd_cols_r36<0, 1250>, sizeof(float2) * (8 * 1346 + 440)) ||
+        set_smem((const void *)fwd_cols_r36<1, 1250>, sizeof(float2) * (8 * 1346 + 440)) ||
+        set_smem((const void *)fwd_cols_r36<2, 1250>, sizeof(float2) * (8 * 1346 + 440)) ||
+        set_smem((const void *)fwd_rows_v2<false, 1296, false>, sv2)) {
       kgpu_master_destroy(m);
       return nullptr;
     }
@@ -532,12 +563,11 @@ extern "C" void kgpu_master_destroy(kgpu_master *m) {
   if (!m) return;
   cudaFree(m->d_items);
   cudaFree(m->d_rootD);
-  cudaFree(m->d_twA);
-  cudaFree(m->d_twB);
   cudaFree(m->d_rootC);
-  cudaFree(m->d_twA64);
-  cudaFree(m->d_twB64);
   cudaFree(m->d_twU);
+  cudaFree(m->d_r36_tw0);
+  cudaFree(m->d_r36_A);
+  cudaFree(m->d_r36_B);
   cudaFree(m->d_twT);
   cudaFree(m->d_mid);
   cudaFree(m->d_notch);
@@ -612,7 +642,7 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
   a1.mid = mid;
   a1.stats = (fmt == KGPU_FMT_I16) ? (IngestStats *)d_stats : nullptr;
   a1.dbg = (unsigned long long *)g_dbg_buf;
-  a1.mid_mod = g_tuning[7].load();
+  a1.mid_mod = 0;
   a1.pf_dist = g_tuning[3].load() >= 2 ? g_tuning[3].load() - 1 : 0;
   dim3 const g1((unsigned)((m->sp.n2 + kTile - 1) / kTile), (unsigned)nblocks);
   if (g_tuning[3].load() == 1) {  // experiment: pull the input windows into L2 with coalesced requests first
@@ -622,15 +652,12 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
     g_launches++;
   }
   FwdTables tb;
-  tb.twA = m->d_twA;
-  tb.twB = m->d_twB;
   tb.rootC = m->d_rootC;
-  tb.nit = m->nit;
   bool const use_static = g_static_on.load() != 0;
   bool halved = false;
   {
     ProfScope ps(K_FWD_COLS, st);
-    if (use_static && m->static_cols == 1296 && g_tuning[5].load() != 1) {
+    if (use_static && m->static_cols == 1296) {
       int const f = (fmt != KGPU_FMT_I16) ? 0 : ((derandomize || a1.stats) ? 2 : 1);
       size_t const sv1 = sizeof(float2) * (8 * 1298 + 1288 + 80);
       ColsV2Tables t2;
@@ -644,11 +671,15 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
         if (f == 0) fwd_cols_v2<0, 1250, 0, true><<<g1, 288, sv1 + 128, st>>>(a1, t2, m->mid_map);
         else if (f == 1) fwd_cols_v2<1, 1250, 0, true><<<g1, 288, sv1 + 128, st>>>(a1, t2, m->mid_map);
         else fwd_cols_v2<2, 1250, 0, true><<<g1, 288, sv1 + 128, st>>>(a1, t2, m->mid_map);
-      } else if (m->sp.n2 == 1250 && f != 0 && g_tuning[9].load() == 1) {  // persistent, next tile's words in flight
-        int const tpb = (int)g1.x, ntiles = tpb * nblocks;
-        int const grid = std::min(2 * sm_count(), ntiles);
-        if (f == 1) fwd_cols_v3<1, 1250><<<grid, 288, sv1, st>>>(a1, t2, tpb, ntiles);
-        else fwd_cols_v3<2, 1250><<<grid, 288, sv1, st>>>(a1, t2, tpb, ntiles);
+      } else if (m->sp.n2 == 1250 && g_tuning[13].load() == 3) {  // two fat stages (36 x 36), one trip through shared memory
+        size_t const sr = sizeof(float2) * (8 * 1346 + 440);
+        ColsR36Tables t3;
+        t3.tw0 = m->d_r36_tw0;
+        t3.twA = m->d_r36_A;
+        t3.twB = m->d_r36_B;
+        if (f == 0) fwd_cols_r36<0, 1250><<<g1, 288, sr, st>>>(a1, t3);
+        else if (f == 1) fwd_cols_r36<1, 1250><<<g1, 288, sr, st>>>(a1, t3);
+        else fwd_cols_r36<2, 1250><<<g1, 288, sr, st>>>(a1, t3);
       } else if (m->sp.n2 == 1250 && f == 1 && g_tuning[13].load() == 2) {  // 6-column tiles, three CTAs per SM
         size_t const sv6 = sizeof(float2) * (6 * 1298 + 1288 + 60);
         dim3 const g6((unsigned)((m->sp.n2 + 5) / 6), (unsigned)nblocks);
@@ -667,29 +698,6 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
         if (f == 0) fwd_cols_v2<0><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
         else if (f == 1) fwd_cols_v2<1><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
         else fwd_cols_v2<2><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
-      }
-    } else if (use_static && m->static_cols == 12960 && fmt == KGPU_FMT_I16) {
-      size_t const s1 = sizeof(float2) * ((size_t)8 * static_pitch(phys_len<S1296b>()) + static_tw_count<S1296b>() + 2 + 8 * 42);
-      fwd_cols_static<1, S1296b, 8, 1, 0, 2><<<g1, 256, s1, st>>>(a1, tb);
-    } else if (use_static && m->static_cols == 1296) {
-      int const wpc = g_tuning[0].load() == 1 ? 1 : 2;
-      int const f = (fmt != KGPU_FMT_I16) ? 0 : ((derandomize || a1.stats) ? 2 : 1);
-      bool const lay1 = (wpc == 2 && f == 1 && g_tuning[2].load() != 2);
-      size_t const s1 = sizeof(float2) * ((size_t)8 * (lay1 ? 1312 : m->pitch1) + static_tw_count<S1296>() + 2 + 8 * 42);
-      if (wpc == 1) {
-        if (f == 0) fwd_cols_static<0, S1296, 8, 1><<<g1, 256, s1, st>>>(a1, tb);
-        else if (f == 1) fwd_cols_static<1, S1296, 8, 1><<<g1, 256, s1, st>>>(a1, tb);
-        else fwd_cols_static<2, S1296, 8, 1><<<g1, 256, s1, st>>>(a1, tb);
-      } else {
-        FwdTables t2 = tb;
-        t2.twA = m->d_twA64;
-        t2.twB = m->d_twB64;
-        t2.nit = m->nit64;
-        if (f == 0) fwd_cols_static<0, S1296, 8, 2><<<g1, 512, s1, st>>>(a1, t2);
-        else if (f == 1 && g_tuning[2].load() != 2 && g_tuning[4].load() != 2) fwd_cols_static<1, S1296, 8, 2, 1, 2, true><<<g1, 512, s1, st>>>(a1, t2);
-        else if (f == 1 && g_tuning[2].load() != 2) fwd_cols_static<1, S1296, 8, 2, 1><<<g1, 512, s1, st>>>(a1, t2);
-        else if (f == 1) fwd_cols_static<1, S1296, 8, 2><<<g1, 512, s1, st>>>(a1, t2);
-        else fwd_cols_static<2, S1296, 8, 2><<<g1, 512, s1, st>>>(a1, t2);
       }
     } else if (fmt == KGPU_FMT_I16)
       fwd_cols_kernel<1><<<g1, kFwdThreads, m->smem1, st>>>(a1);
@@ -710,36 +718,17 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
   a2.spec = (float2 *)d_spec;
   a2.spec_stride = m->spec_stride;
   a2.dbg = g_dbg_buf2 ? (unsigned long long *)g_dbg_buf2 : nullptr;
-  a2.mid_mod = g_tuning[7].load();
+  a2.mid_mod = 0;
   dim3 const g2((unsigned)m->n_item_ctas, (unsigned)nblocks);
   {
     ProfScope ps(K_FWD_ROWS, st);
-    if (use_static && m->static_rows == 1250 && g_tuning[5].load() != 1) {
+    if (use_static && m->static_rows == 1250) {
       size_t const sv2 = sizeof(float2) * (8 * 1250 + 1246);
-      if (g_tuning[8].load() == 1) {  // persistent: one CTA per SM walks over the tiles
-        size_t const sv3 = sizeof(float2) * (2 * 8 * 1250 + 1246);
-        int const ntiles = m->n_item_ctas * nblocks;
-        int const grid = std::min(sm_count(), ntiles);
-        if (a2.real_split && halved) fwd_rows_v3<true, 1296, true><<<grid, 512, sv3, st>>>(a2, tb, m->n_item_ctas, ntiles);
-        else if (a2.real_split) fwd_rows_v3<true, 0, false><<<grid, 512, sv3, st>>>(a2, tb, m->n_item_ctas, ntiles);
-        else if (m->sp.n1 == 1296) fwd_rows_v3<false, 1296, false><<<grid, 512, sv3, st>>>(a2, tb, m->n_item_ctas, ntiles);
-        else fwd_rows_v3<false, 0, false><<<grid, 512, sv3, st>>>(a2, tb, m->n_item_ctas, ntiles);
-      } else if (a2.real_split && halved && g_tuning[10].load() == 1) fwd_rows_v2<true, 1296, true, true><<<g2, 256, sv2, st>>>(a2, tb);
+      if (a2.real_split && halved && g_tuning[10].load() == 1) fwd_rows_v2<true, 1296, true, true><<<g2, 256, sv2, st>>>(a2, tb);
       else if (a2.real_split && halved) fwd_rows_v2<true, 1296, true><<<g2, 256, sv2, st>>>(a2, tb);
       else if (a2.real_split) fwd_rows_v2<true><<<g2, 256, sv2, st>>>(a2, tb);
       else if (m->sp.n1 == 1296) fwd_rows_v2<false, 1296, false><<<g2, 256, sv2, st>>>(a2, tb);
       else fwd_rows_v2<false><<<g2, 256, sv2, st>>>(a2, tb);
-    } else if (use_static && m->static_rows == 1250) {
-      size_t const s2 = sizeof(float2) * ((size_t)kTile * m->pitch2 + static_tw_count<S1250>());
-      bool const w2 = g_tuning[1].load() != 1;
-      if (a2.real_split) {
-        if (w2 && g_tuning[4].load() != 2) fwd_rows_static<S1250, true, 2, true><<<g2, 512, s2, st>>>(a2, tb);
-        else if (w2) fwd_rows_static<S1250, true, 2><<<g2, 512, s2, st>>>(a2, tb);
-        else fwd_rows_static<S1250, true, 1><<<g2, 256, s2, st>>>(a2, tb);
-      } else {
-        if (w2) fwd_rows_static<S1250, false, 2><<<g2, 512, s2, st>>>(a2, tb);
-        else fwd_rows_static<S1250, false, 1><<<g2, 256, s2, st>>>(a2, tb);
-      }
     } else
       fwd_rows_kernel<<<g2, kFwdThreads, m->smem2, st>>>(a2);
   }
@@ -930,6 +919,8 @@ struct kgpu_bank {
   int *d_order = nullptr;
   ChanAux *d_aux = nullptr;   // [capacity]
   int *d_shift = nullptr;     // [capacity] shifts, for the noise estimator
+  float2 *d_fm_mem[2] = {nullptr, nullptr};  // [capacity] discriminator phase memory, ping-pong per launch
+  int fm_parity = 0;
   std::vector<ChanAux> aux;
   long block_counter = 0;     // index of the next block a run will process (oscillator epoch arithmetic)
   long last_rebase = 0;
@@ -1075,6 +1066,10 @@ extern "C" kgpu_bank *kgpu_bank_create(kgpu_master *m, int capacity) {
   CUDA_OKP(cudaMalloc(&b->d_order, sizeof(int) * (size_t)capacity));
   CUDA_OKP(cudaMalloc(&b->d_aux, sizeof(ChanAux) * (size_t)capacity));
   CUDA_OKP(cudaMalloc(&b->d_shift, sizeof(int) * (size_t)capacity));
+  for (int i = 0; i < 2; i++) {
+    CUDA_OKP(cudaMalloc(&b->d_fm_mem[i], sizeof(float2) * (size_t)capacity));
+    CUDA_OKP(cudaMemset(b->d_fm_mem[i], 0, sizeof(float2) * (size_t)capacity));
+  }
   return b;
 }
 extern "C" void kgpu_bank_destroy(kgpu_bank *b) {
@@ -1084,6 +1079,8 @@ extern "C" void kgpu_bank_destroy(kgpu_bank *b) {
   cudaFree(b->d_order);
   cudaFree(b->d_aux);
   cudaFree(b->d_shift);
+  cudaFree(b->d_fm_mem[0]);
+  cudaFree(b->d_fm_mem[1]);
   delete b;
 }
 static bool bad_idx(kgpu_bank const *b, int idx) { return !b || idx < 0 || idx >= b->capacity; }
@@ -1264,19 +1261,6 @@ template <class P> static int launch_chan_v2(ChanArgs const &a, int n, int nbloc
   return 0;
 }
 
-template <class P> static int launch_chan_v3(ChanArgs const &a, int n, int nblocks, cudaStream_t st) {
-  constexpr int R0 = P::rad(0), S0 = P::len / R0, TPC = 128 / (S0 > R0 ? S0 : R0);
-  size_t const sm = sizeof(float2) * ((size_t)(2 * P::len + 6) * TPC + static_tw_count<P>() + 2);
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (set_smem((const void *)chan_v3<P>, sm)) return -1;
-    attr_done = true;
-  }
-  dim3 const g((unsigned)((n + TPC - 1) / TPC), (unsigned)nblocks);
-  chan_v3<P><<<g, 128, sm, st>>>(a);
-  return 0;
-}
-
 template <class P> static int launch_chan_static(ChanArgs const &a, int n, int nblocks, cudaStream_t st) {
   size_t const sm = sizeof(float2) * ((size_t)(2 * P::len + 4) * kChanWarps + static_tw_count<P>() + 2);
   static bool attr_done = false;
@@ -1314,17 +1298,8 @@ static int launch_chan(kgpu_bank *b, const void *d_spec, int nblocks, void *d_ou
   g_launches++;
   TilePlan const *tp = host_tile_plan(plan);
   if (g_static_on.load() && !generic) {
-    if (g_tuning[6].load() == 2 && !a.wrap && !b->any_osc) {  // lane-packed variant: REAL master, no ISB channel in the bank
-      bool isb = false;
-      for (int i = 0; i < b->nchan && !isb; i++) isb = b->ch[(size_t)i].defined && (b->ch[(size_t)i].flags & 1);
-      if (!isb && plan_is<S600>(tp)) return launch_chan_v3<S600>(a, n, nblocks, st);
-    }
-    if (g_tuning[6].load() != 1) {
-      if (plan_is<S600>(tp)) return launch_chan_v2<S600>(a, n, nblocks, st, b->any_osc);
-      if (plan_is<S300>(tp)) return launch_chan_v2<S300>(a, n, nblocks, st, b->any_osc);
-    }
-    if (plan_is<S600>(tp)) return launch_chan_static<S600>(a, n, nblocks, st);
-    if (plan_is<S300>(tp)) return launch_chan_static<S300>(a, n, nblocks, st);
+    if (plan_is<S600>(tp)) return launch_chan_v2<S600>(a, n, nblocks, st, b->any_osc);
+    if (plan_is<S300>(tp)) return launch_chan_v2<S300>(a, n, nblocks, st, b->any_osc);
     if (plan_is<S1200>(tp)) return launch_chan_static<S1200>(a, n, nblocks, st);
   }
   size_t const sm = sizeof(float2) * (size_t)a.pitch * kChanWarps;
@@ -1392,6 +1367,33 @@ extern "C" int kgpu_bank_noise(kgpu_bank *b, const void *d_spec, int nblocks, do
   {
     ProfScope ps(K_NOISE, st);
     noise_kernel<<<dim3((unsigned)b->nchan, (unsigned)nblocks), kNoiseThreads, 0, st>>>(a);
+  }
+  g_launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+// FM discriminator front half on the channel outputs of the run that just filled d_out (fm.c:104-131, :205-231).
+extern "C" int kgpu_bank_fm_front(kgpu_bank *b, const void *d_out, long out_pitch, int nblocks, float *d_baseband, double *d_stats,
+                                  void *stream) {
+  if (!b || !d_out || !d_baseband || !d_stats || nblocks < 1 || out_pitch < 0) return fail("kgpu_bank_fm_front: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bank_commit(b, st)) return -1;
+  if (b->nchan == 0) return 0;
+  FmArgs a;
+  a.out = (float2 const *)d_out;
+  a.out_pitch = out_pitch ? out_pitch : b->out_stride;
+  a.desc = b->d_desc;
+  a.nblocks = nblocks;
+  a.mem_in = b->d_fm_mem[b->fm_parity];
+  a.mem_out = b->d_fm_mem[b->fm_parity ^ 1];
+  a.baseband = d_baseband;
+  a.bb_pitch = 2 * a.out_pitch;
+  a.stats = (double2 *)d_stats;
+  a.stats_stride = b->capacity;
+  b->fm_parity ^= 1;
+  {
+    ProfScope ps(K_NOISE, st);
+    fm_front_kernel<<<dim3((unsigned)b->nchan, (unsigned)nblocks), kFmThreads, 0, st>>>(a);
   }
   g_launches++;
   CUDA_OK(cudaGetLastError());

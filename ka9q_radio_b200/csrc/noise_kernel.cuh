@@ -184,4 +184,65 @@ __global__ void __launch_bounds__(kNoiseThreads) noise_kernel(NoiseArgs const a)
   }
 }
 
+
+// ------------------------------------------------------------------ FM discriminator front half -----------------------
+// Replaces the per-sample loops at the top of demod_fm (reference fm.c:104-131 and :205-231, plain discriminator): for every
+// channel and block, baseband[n] = arg(y[n] conj y[n-1]) / pi with y[-1] carried over from the previous block, the mean
+// amplitude and the sum of squared amplitude deviations (two passes, as the reference).  Reads the channel kernel's output
+// rows in place; one CTA per (channel, block).
+constexpr int kFmThreads = 128;
+struct FmArgs {
+  float2 const *out;   // channel outputs [block][out_pitch]
+  long out_pitch;
+  ChanDesc const *desc;
+  int nblocks;
+  float2 const *mem_in;  // [channel] last sample of the block before this launch (0 at start)
+  float2 *mem_out;       // [channel] last sample of this launch's last block
+  float *baseband;       // [block][bb_pitch], channel i's olen floats at 2 * desc[i].out_off (same packing as the outputs)
+  long bb_pitch;
+  double2 *stats;        // [block][stats_stride]: (.x mean amplitude, .y sum of squared deviations)
+  long stats_stride;
+};
+__global__ void __launch_bounds__(kFmThreads) fm_front_kernel(FmArgs const a) {
+  __shared__ double red[kFmThreads / 32];
+  __shared__ double mean_sh;
+  int const ci = blockIdx.x, blk = blockIdx.y, tid = threadIdx.x;
+  ChanDesc const d = a.desc[ci];
+  if (d.plan < 0 || (d.flags & kChanRealOut) || d.olen <= 0) return;
+  float2 const *y = a.out + (long)blk * a.out_pitch + d.out_off;
+  float2 const first_prev = blk > 0 ? a.out[(long)(blk - 1) * a.out_pitch + d.out_off + d.olen - 1] : a.mem_in[ci];
+  float *bb = a.baseband + (long)blk * a.bb_pitch + 2 * d.out_off;
+  double sum = 0;
+  for (int n = tid; n < d.olen; n += kFmThreads) {
+    float2 const v = y[n];
+    float2 const p = n > 0 ? y[n - 1] : first_prev;
+    double const re = (double)v.x * p.x + (double)v.y * p.y, im = (double)v.y * p.x - (double)v.x * p.y;  // v * conj(p)
+    bb[n] = (float)(atan2(im, re) * 0.31830988618379067154);
+    sum += (double)hypotf(v.x, v.y);
+  }
+  auto block_sum = [&](double v) -> double {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double t = 0;
+    for (int w = 0; w < kFmThreads / 32; w++) t += red[w];
+    return t;
+  };
+  double const mean = block_sum(sum) / (double)d.olen;
+  double dev = 0;
+  for (int n = tid; n < d.olen; n += kFmThreads) {
+    float2 const v = y[n];
+    double const e = (double)hypotf(v.x, v.y) - mean;
+    dev += e * e;
+  }
+  dev = block_sum(dev);
+  if (tid == 0) {
+    a.stats[(long)blk * a.stats_stride + ci] = make_double2(mean, dev);
+    if (blk == a.nblocks - 1) a.mem_out[ci] = y[d.olen - 1];
+  }
+  (void)mean_sh;
+}
+
 }  // namespace kfft

@@ -106,6 +106,13 @@ double ko_finetune_block(struct ko_finetune *s, int L, int M, int shift, double 
 /* noise density estimate from the master spectrum (radio.c:1783-1866; quantile :1722-1775) */
 double ko_estimate_noise(int in_type, int m_bins, float complex const *X, int s_bins, int shift, double samprate);
 
+/* FM discriminator front half (fm.c:104-131 amplitude statistics, fm.c:205-231 arg(x[n] conj x[n-1]) / pi); restated only */
+void ko_fm_front(float complex const *x, int n, double complex *phase_memory, float *baseband, double *avg_amp,
+                 double *variance_sum);
+
+/* Airspy R2 / HydraSDR packed 12-bit ingest (airspy-unpack.c:106-130) */
+int ko_airspy_unpack(float *dst, uint32_t const *packed, int sampcount, float scale, uint64_t *energy);
+
 #ifdef __cplusplus
 }
 #endif

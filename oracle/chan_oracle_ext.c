@@ -295,6 +295,59 @@ double ko_estimate_noise(int in_type, int m_bins, float complex const *X, int s_
   return energy * correction / ((double)m_bins * samprate);
 }
 
+/* ---------------------------------------------------------------- Airspy 12-bit packed ingest ---------- */
+/* airspy-unpack.c:106-130 (portable version; the AVX2 one :17-104 computes the same): 8 offset-binary 12-bit samples in
+ * three 32-bit words, most significant first; x = s - 2048, float = scale * x, energy += x*x, clip count x == 2047 or
+ * x <= -2047.  sampcount must be a multiple of 8.  Returns the clip count. */
+int ko_airspy_unpack(float *dst, uint32_t const *up, int sampcount, float scale, uint64_t *energy) {
+  int over = 0;
+  for (int i = 0; i < sampcount; i += 8, up += 3, dst += 8) {
+    uint32_t s[8];
+    s[0] = up[0] >> 20;
+    s[1] = up[0] >> 8;
+    s[2] = (up[0] << 4) | (up[1] >> 28);
+    s[3] = up[1] >> 16;
+    s[4] = up[1] >> 4;
+    s[5] = (up[1] << 8) | (up[2] >> 24);
+    s[6] = up[2] >> 12;
+    s[7] = up[2];
+    for (int j = 0; j < 8; j++) {
+      int const x = (int)(s[j] & 0xfff) - 2048;
+      over += (x == 2047 || x <= -2047);
+      dst[j] = scale * (float)x;
+      if (energy)
+        *energy += (uint64_t)((int64_t)x * x);
+    }
+  }
+  return over;
+}
+
 /* ---------------------------------------------------------------- FM front half -------------- */
-/* fm.c:104-131 (amplitude statistics for the SNR estimate) and fm.c:205-231 (quadrature discriminator by
- * arg(x[n] conj x[n-1])): see ko_fm_block in chan_oracle_fm.c */
+/* fm.c:104-131 (amplitude statistics of the variance-based SNR estimator: mean of cabsf, then the sum of squared
+ * deviations in a second pass) and fm.c:205-231 (plain quadrature discriminator, no PLL, no threshold extension):
+ *   s = x[n] conj(x[n-1]) in double complex, phase = carg(s) / pi, x[-1] = phase_memory carried across blocks (0 at start).
+ * demod_fm() cannot be isolated from the rest of radiod (squelch, PL, de-emphasis, RTP output in one loop), so this part
+ * is restated from the source only: PARITY UNPINNED for this function. */
+void ko_fm_front(float complex const *x, int n, double complex *phase_memory, float *baseband, double *avg_amp,
+                 double *variance_sum) {
+  double avg = 0;
+  double *amp = malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+  for (int i = 0; i < n; i++)
+    avg += amp[i] = cabsf(x[i]); /* fm.c:117 */
+  avg /= n;
+  double var = 0;
+  for (int i = 0; i < n; i++) /* fm.c:122-123 */
+    var += (amp[i] - avg) * (amp[i] - avg);
+  free(amp);
+  if (avg_amp)
+    *avg_amp = avg;
+  if (variance_sum)
+    *variance_sum = var;
+  double complex pm = *phase_memory;
+  for (int i = 0; i < n; i++) { /* fm.c:211-229 with fm.threshold == false */
+    double complex const s = x[i] * conj(pm);
+    baseband[i] = (float)(M_1_PI * carg(s));
+    pm = x[i];
+  }
+  *phase_memory = pm;
+}

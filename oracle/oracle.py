@@ -70,6 +70,9 @@ def lib() -> C.CDLL:
         L.ko_osc_set.restype = None
         L.ko_estimate_noise.argtypes = [C.c_int, C.c_int, _c64p, C.c_int, C.c_int, C.c_double]
         L.ko_estimate_noise.restype = C.c_double
+        L.ko_fm_front.argtypes = [_c64p, C.c_int, C.c_void_p, _f32p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ko_fm_front.restype = None
+        L.ko_airspy_unpack.argtypes = [_f32p, C.c_void_p, C.c_int, C.c_float, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -199,6 +202,38 @@ def estimate_noise(in_type, spectrum, s_bins, shift, samprate) -> float:
     """radio.c:1783-1866 on one block's master spectrum."""
     return float(lib().ko_estimate_noise(in_type, len(spectrum), np.ascontiguousarray(spectrum, np.complex64),
                                          int(s_bins), int(shift), float(samprate)))
+
+
+class FmFront:
+    """fm.c:104-131 + :205-231 on successive blocks of one channel (phase_memory carried across blocks)"""
+
+    def __init__(self):
+        self.pm = (C.c_double * 2)(0.0, 0.0)
+
+    def block(self, x: np.ndarray):
+        x = np.ascontiguousarray(x, np.complex64)
+        bb = np.empty(len(x), np.float32)
+        avg, var = C.c_double(0), C.c_double(0)
+        lib().ko_fm_front(x, len(x), C.cast(self.pm, C.c_void_p), bb, C.byref(avg), C.byref(var))
+        return bb, avg.value, var.value
+
+
+def airspy_unpack(packed_words: np.ndarray, sampcount: int, scale: float):
+    """airspy-unpack.c:106-130 -> (float32[sampcount], energy, clip count)"""
+    w = np.ascontiguousarray(packed_words, np.uint32)
+    out = np.empty(sampcount, np.float32)
+    e = C.c_uint64(0)
+    over = lib().ko_airspy_unpack(out, w.ctypes.data, sampcount, scale, C.byref(e))
+    return out, int(e.value), over
+
+
+def airspy_pack(samples12: np.ndarray) -> np.ndarray:
+    """inverse of the unpacker, for building test inputs: offset-binary 12-bit values (0..4095), 8 per 3 words"""
+    s = np.asarray(samples12, np.uint64).reshape(-1, 8)
+    w0 = (s[:, 0] << 20) | (s[:, 1] << 8) | (s[:, 2] >> 4)
+    w1 = ((s[:, 2] & 0xF) << 28) | (s[:, 3] << 16) | (s[:, 4] << 4) | (s[:, 5] >> 8)
+    w2 = ((s[:, 5] & 0xFF) << 24) | (s[:, 6] << 12) | s[:, 7]
+    return np.stack([w0, w1, w2], axis=1).astype(np.uint32).reshape(-1)
 
 
 class FineTune:

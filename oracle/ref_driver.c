@@ -23,6 +23,7 @@
 #include <time.h>
 #include "filter.h" /* the reference's header, found through -iquote /root/reference/src */
 #include "osc.h"
+#include "airspy.h"
 
 int Verbose = 0; /* referenced by misc.c */
 char const *App_path = "ka9q-oracle";
@@ -288,4 +289,14 @@ static double ref_bench_run(struct ref_session *s, int L, int in_type, int nchan
   nanosleep(&ts, NULL);
   ref_close(s);
   return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+/* the reference's own unpackers (airspy-unpack.c), both variants, for pinning ko_airspy_unpack */
+int ref_airspy_unpack(float *dst, uint32_t const *up, int sampcount, float scale, uint64_t *energy, int avx2) {
+#if defined(__x86_64__)
+  if (avx2 && __builtin_cpu_supports("avx2"))
+    return airspy_unpack_avx2(dst, up, sampcount, scale, energy);
+#endif
+  (void)avx2;
+  return airspy_unpack(dst, up, sampcount, scale, energy);
 }

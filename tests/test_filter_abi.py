@@ -75,7 +75,8 @@ def test_struct_layout_matches_reference_header():
 # ------------------------------------------------------------------ GPU behaviour ---------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("driver", ["driver_gpuhdr.so", "driver_refhdr.so"])
-def test_radiod_style_flow_matches_oracle(oracle, cuda_dev, driver):
+def test_radiod_style_flow_matches_oracle(oracle, cuda_dev, driver, monkeypatch):
+    monkeypatch.setenv("KA9Q_GPU_SPECTRUM_D2H", "all")   # this test reads the WHOLE of master->fdomain[]
     lib = _load(driver)
     if lib is None:
         pytest.skip(f"{driver} not built")
@@ -91,6 +92,32 @@ def test_radiod_style_flow_matches_oracle(oracle, cuda_dev, driver):
         assert np.abs(gspec[b] - rspec[b]).max() / np.abs(rspec[b]).max() < TOL   # master->fdomain[] on the host
         for c in range(len(chans)):
             assert np.abs(got[b][c] - ref[b][c]).max() / np.abs(ref[b][c]).max() < TOL, (b, c)
+
+
+@pytest.mark.gpu
+def test_default_spectrum_readback_covers_what_estimate_noise_reads(oracle, cuda_dev, monkeypatch):
+    """Default KA9Q_GPU_SPECTRUM_D2H=windows: master->fdomain[] holds, for every slave, the >= 1000 bins around |shift| that
+    the untouched estimate_noise() (radio.c:1805-1836) reads -- checked by running the oracle's restatement of it on the
+    host copy -- without copying the other 1.6 M bins."""
+    monkeypatch.delenv("KA9Q_GPU_SPECTRUM_D2H", raising=False)
+    lib = _load("driver_gpuhdr.so")
+    L, M, fs = 48000, 12001, 2.4e6
+    x = oracle.siggen_real(4 * L, 0.1, 0.02, 0.25, 1.0)
+    shifts = [15000, -9000, 300, 29900]
+    with oracle.RefSession(L, M, oracle.KO_REAL, lib=lib) as s:
+        ids = [s.add_channel(480, -1 / 3, 1 / 3, 11.0) for _ in shifts]
+        for b in range(4):
+            assert s.write(x[b * L:(b + 1) * L]) == 1
+            for i, sh in zip(ids, shifts):
+                s.execute(i, sh)
+            host = s.spectrum()
+            X = oracle.forward(oracle.block_window(x, L, M, b))
+            if b >= 1:   # the windows follow the shifts the slaves used on the previous block
+                for sh in shifts:
+                    a = oracle.estimate_noise(oracle.KO_REAL, host, 600, sh, fs)
+                    r = oracle.estimate_noise(oracle.KO_REAL, X, 600, sh, fs)
+                    assert abs(a - r) / r < 1e-5
+                assert not host[20000:25000].any()   # far from every channel: never copied
 
 
 @pytest.mark.gpu

@@ -114,7 +114,8 @@ def test_forward_linearity_and_impulse(oracle, cuda_dev):
     cz.forward(cz.stage_stream(b), 1, sb)
     cz.forward(cz.stage_stream(a + b), 1, sab)
     torch.cuda.synchronize()
-    err = (sab - sa - sb).abs().max().item() / sab.abs().max().item()
+    nbin = cz.master.bins  # the rows are padded to a multiple of 4 bins: the padding is never written
+    err = (sab - sa - sb)[:, :nbin].abs().max().item() / sab[:, :nbin].abs().max().item()
     assert err < 2e-6
     cz.close()
 

@@ -79,6 +79,26 @@ def _worker(rank, world, port, tmp):
         if rank == 0:  # every push is acknowledged before its slot's channels and before the slot is refilled
             assert [e for e in log if e[0] == "push"] == [("push", k % 2) for k in range(nsteps)]
             assert [e for e in log if e[0] == "ready"] == [("ready", k % 2) for k in range(nsteps)]
+    elif os.environ.get("KA_SHARDER") == "allgather":
+        # block-parallel forward: a step is `world` blocks, rank r transforms block step*world + r, ONE all-gather per
+        # step hands every block's spectrum to everybody (bench.py --mg-mode allgather)
+        nst = nsteps // world
+        spec2 = [torch.zeros((world, N // 2 + 1), dtype=torch.complex64) for _ in range(2)]
+
+        def forward_part(step, slot):
+            spec2[slot][rank].copy_(torch.from_numpy(O.forward(O.block_window(x, L, M, step * world + rank))))
+
+        def gather(slot):
+            parts = [spec2[slot][r] for r in range(world)]
+            return dist.all_gather(parts, spec2[slot][rank].clone(), async_op=True)
+
+        def channels_ag(step, slot):
+            for r in range(world):
+                X = spec2[slot][r].numpy()
+                for i in mine:
+                    out[(step * world + r, i)] = O.channel_block(O.KO_REAL, X, resp[i], chans[i]["shift"])[-48:].copy()
+
+        PipelinedSharder(rank, world, forward_part, gather, channels_ag, forward_on_all=True).run(range(nst))
     else:
         PipelinedSharder(rank, world, forward, broadcast, channels).run(range(nsteps))
     np.save(Path(tmp) / f"rank{rank}.npy", {k: v for k, v in out.items()}, allow_pickle=True)
@@ -86,12 +106,12 @@ def _worker(rank, world, port, tmp):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("sharder", ["pipelined", "multicast"])
+@pytest.mark.parametrize("sharder", ["pipelined", "multicast", "allgather"])
 def test_two_rank_gloo_pipeline_matches_single_process(tmp_path, oracle, sharder, monkeypatch):
     import torch.multiprocessing as mp
 
     monkeypatch.setenv("KA_SHARDER", sharder)
-    port = 29600 + (os.getpid() % 300) + (17 if sharder == "multicast" else 0)
+    port = 29600 + (os.getpid() % 300) + {"pipelined": 0, "multicast": 17, "allgather": 31}[sharder]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     got = {}
     for r in range(2):
@@ -100,6 +120,7 @@ def test_two_rank_gloo_pipeline_matches_single_process(tmp_path, oracle, sharder
     x = oracle.siggen_real(nsteps * L, 0.1, 0.02, 0.27, 1.0)
     chans = [dict(olen=48, shift=900 + 200 * i, low=-0.3, high=0.3, beta=9.0) for i in range(7)]
     ref, _ = oracle.run_stream(x, L, M, chans)
-    assert len(got) == nsteps * len(chans)
+    nexp = nsteps if sharder != "allgather" else (nsteps // 2) * 2
+    assert len(got) == nexp * len(chans)
     for (step, i), y in got.items():
         assert np.array_equal(y, ref[step][i])

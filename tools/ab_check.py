@@ -6,7 +6,8 @@ from pathlib import Path
 import numpy as np, torch
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-import bench
+from ka9q_radio_b200 import workloads
+W = workloads.cfg2()
 from ka9q_radio_b200 import capi
 from ka9q_radio_b200.channelizer import Channelizer
 lib = capi.load(); dev = torch.device("cuda:0")
@@ -17,7 +18,7 @@ def setv(v):
             k, val = kv.split("="); lib.kgpu_set_tuning(int(k), int(val))
 B = 5
 rng = np.random.default_rng(1)
-for name, in_type, L, M in (("real-i16", capi.KGPU_REAL, bench.L, bench.M), ("complex-f32", capi.KGPU_COMPLEX, bench.L // 2, (bench.M - 1) // 2 + 1)):
+for name, in_type, L, M in (("real-i16", capi.KGPU_REAL, W.L, W.M), ("complex-f32", capi.KGPU_COMPLEX, W.L // 2, (W.M - 1) // 2 + 1)):
     cz = Channelizer(L, M, in_type, dev, capacity=64)
     nch = 43
     for k in range(nch):  # upright, inverted and band-edge channels (REAL: |shift| < N/2; COMPLEX: wraps)
@@ -29,11 +30,11 @@ for name, in_type, L, M in (("real-i16", capi.KGPU_REAL, bench.L, bench.M), ("co
         x = (rng.standard_normal(B * L) + 1j * rng.standard_normal(B * L)).astype(np.complex64)
     d = cz.stage_stream(x)
     ref = cz.alloc_spectra(B); oref = cz.alloc_outputs(B); setv("default")
-    cz.forward(d, B, ref, scale=bench.SCALE); cz.channels(ref, B, oref); torch.cuda.synchronize()
+    cz.forward(d, B, ref, scale=W.scale); cz.channels(ref, B, oref); torch.cuda.synchronize()
     print(name, cz.master.describe())
     for v in sys.argv[1:]:
         out = cz.alloc_spectra(B); out.zero_(); oo = cz.alloc_outputs(B); oo.zero_(); setv(v)
-        cz.forward(d, B, out, scale=bench.SCALE); cz.channels(out, B, oo); torch.cuda.synchronize()
+        cz.forward(d, B, out, scale=W.scale); cz.channels(out, B, oo); torch.cuda.synchronize()
         nb = cz.master.bins
         diff = (out[:, :nb] - ref[:, :nb]).abs().max().item(); mag = ref[:, :nb].abs().max().item()
         od = (oo - oref).abs().max().item(); om = oref.abs().max().item()

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 #include "ka9q_gpu_filter.h"
 
 static double now_s(void) {
@@ -27,7 +28,7 @@ struct run {
   struct filter_out *out;
   struct filter_out **outp;
   int *shifts;
-  int nchan, k, nblocks, warm;
+  int nchan, k, nblocks, warm, inplace;
   int16_t const *stream;
   long stream_blocks; /* blocks available in `stream`, replayed cyclically */
   long words_per_block;
@@ -44,7 +45,7 @@ static void *producer(void *p) {
     int k = r->k;
     if (k > total - b)
       k = total - b;
-    if (pos + k > r->stream_blocks)
+    if (!r->inplace && pos + k > r->stream_blocks)
       pos = 0;
     /* ADC pacing stand-in: never overwrite a ring slot a slave has not consumed (an unpaced producer would only
      * make every channel drop blocks, filter.c:690-701) */
@@ -61,8 +62,9 @@ static void *producer(void *p) {
     double const t = now_s();
     for (int j = 0; j < k; j++)
       r->t_write[b + j] = t;
-    write_i16filter(&r->in, r->stream + pos * r->words_per_block, (int)(k * (r->words_per_block / (r->in.in_type == COMPLEX ? 2 : 1))),
-                    r->scale, false);
+    /* inplace: the samples are already in the pinned ring (a driver's DMA target, filter_i16_write_pointer): publish only */
+    write_i16filter(&r->in, r->inplace ? NULL : r->stream + pos * r->words_per_block,
+                    (int)(k * (r->words_per_block / (r->in.in_type == COMPLEX ? 2 : 1))), r->scale, false);
     pos += k;
     b += k;
   }
@@ -83,12 +85,21 @@ static void *consumer(void *p) {
   return NULL;
 }
 
+/* int16 words in the library's raw-ingest ring: ND windows, rounded up to whole pages (filter_abi.c: page_round) */
+long kgf_ring_words(int L, int M, int in_type) {
+  size_t const esz = (in_type == COMPLEX) ? 2 * sizeof(int16_t) : sizeof(int16_t);
+  size_t const pg = (size_t)sysconf(_SC_PAGESIZE);
+  size_t const bytes = ((size_t)ND * (size_t)(L + M - 1) * esz + pg - 1) / pg * pg;
+  return (long)(bytes / sizeof(int16_t));
+}
+
 /* Returns seconds for `nblocks` blocks (after `warm` untimed ones), < 0 on error.
  * check_out (nchan * max_olen complex) receives every slave's output of the LAST block; *last_stream_block its index in
  * `stream`; lat_ms[2] = mean and max hand-over -> delivered latency per block; *drops the dropped blocks. */
 double kgf_e2e_run(int L, int M, int in_type, int nchan, int const *olen, int const *shifts, double const *low, double const *high,
                    double const *beta, int16_t const *stream, long stream_blocks, int blocks_per_write, int warm, int nblocks,
-                   float scale, float complex *check_out, int max_olen, long *last_stream_block, double *lat_ms, unsigned *drops) {
+                   float scale, float complex *check_out, int max_olen, long *last_stream_block, double *lat_ms, unsigned *drops,
+                   int inplace) {
   struct run r;
   memset(&r, 0, sizeof r);
   N_worker_threads = 1; /* not inline: producer and consumers are different threads */
@@ -111,6 +122,19 @@ double kgf_e2e_run(int L, int M, int in_type, int nchan, int const *olen, int co
   r.stream_blocks = stream_blocks;
   r.words_per_block = (long)L * (in_type == COMPLEX ? 2 : 1);
   r.scale = scale;
+  r.inplace = 0;
+  long const ring_words = kgf_ring_words(L, M, in_type);
+  if (inplace) {
+    /* Fill the whole pinned ring once (ring_words int16 words, starting at the write pointer and running through the
+     * mirror mapping at the ring's end), as a front end's DMA would keep doing, and let the producer publish the samples
+     * block by block without touching them again: ring[(hist + i) mod R] = stream[i], so block b's window starts at
+     * stream word (b * words_per_block - hist) mod R. */
+    int16_t *w = filter_i16_write_pointer(&r.in);
+    if (w == NULL || stream_blocks * r.words_per_block < ring_words)
+      return -3;
+    memcpy(w, stream, sizeof(int16_t) * (size_t)ring_words);
+    r.inplace = 1;
+  }
   r.t_write = calloc((size_t)(warm + nblocks), sizeof(double));
   r.t_done = calloc((size_t)(warm + nblocks), sizeof(double));
   for (int i = 0; i < nchan; i++)
@@ -147,11 +171,18 @@ double kgf_e2e_run(int L, int M, int in_type, int nchan, int const *olen, int co
       int k = blocks_per_write;
       if (k > total - b)
         k = total - b;
-      if (pos + k > stream_blocks)
+      if (!inplace && pos + k > stream_blocks)
         pos = 0;
       last = pos + k - 1;
       pos += k;
       b += k;
+    }
+    if (inplace) { /* word index (into `stream`, cyclic with period ring_words) of the last block's window start */
+      long const hist = (long)(M - 1) * (in_type == COMPLEX ? 2 : 1);
+      long st = ((long)(total - 1) * r.words_per_block - hist) % ring_words;
+      if (st < 0)
+        st += ring_words;
+      last = st;
     }
     *last_stream_block = last;
   }

@@ -9,7 +9,8 @@ from pathlib import Path
 import numpy as np, torch
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-import bench
+from ka9q_radio_b200 import workloads
+W = workloads.cfg2()
 from ka9q_radio_b200 import capi
 from ka9q_radio_b200.channelizer import Channelizer
 
@@ -23,12 +24,12 @@ a = ap.parse_args()
 lib = capi.load()
 dev = torch.device("cuda:0")
 B = a.blocks
-cz = Channelizer(bench.L, bench.M, capi.KGPU_REAL, dev, capacity=a.nchan)
+cz = Channelizer(W.L, W.M, capi.KGPU_REAL, dev, capacity=a.nchan)
 for k in range(a.nchan):
-    cz.add_channel(bench.OLEN, bench.channel_shift(k), -1 / 3, 1 / 3, 11.0)
+    cz.add_channel(480, W.channels[k % 1024].shift, -1 / 3, 1 / 3, 11.0)
 nstream = max(32, 4 * B)
 rng = np.random.default_rng(0)
-host = rng.integers(-3000, 3000, nstream * bench.L + bench.M - 1, dtype=np.int16)
+host = rng.integers(-3000, 3000, nstream * W.L + W.M - 1, dtype=np.int16)
 d_stream = torch.from_numpy(host).to(dev)
 spec, out = cz.alloc_spectra(B), cz.alloc_outputs(B)
 ng = nstream // B
@@ -48,7 +49,7 @@ for rnd in range(a.rounds + 1):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); e0.record()
         for i in range(a.iters):
-            cz.forward(d_stream, B, spec, scale=bench.SCALE, first_block=(i % ng) * B)
+            cz.forward(d_stream, B, spec, scale=W.scale, first_block=(i % ng) * B)
             cz.channels(spec, B, out)
         e1.record(); torch.cuda.synchronize()
         p = capi.profile_snapshot(); lib.kgpu_profile_enable(0)
