@@ -155,10 +155,11 @@ int kgpu_bank_commit(kgpu_bank *b, void *stream);
  * kernel exists (both are parity-tested). Default 1. */
 int kgpu_use_static_kernels(int on);
 
-/* Experiment knobs for A/B measurements (0 = shipped default). key 0 / 1: warps per column in the
- * cols / rows kernels (1, default 2); key 2: 2 = plain column pitch in the cols kernel (default:
- * bank-conflict-free column bases); key 3: 1 = L2 prefetch of the input before the cols kernel;
- * key 4: 2 = load every stage twiddle (default: load 4, form the rest as products). */
+/* Experiment knobs for A/B measurements (0 = shipped default everywhere).  key 13: column pass of the 1296 x n2
+ * transform: 0 = 36 x 36 two-stage kernel (default), 4 = round-1 12 x 12 x 9 kernel, 1 / 2 = that kernel with 16 / 6-column tiles;
+ * key 2: 1 / 2 = table twiddles / I2F unpack in the 12 x 12 x 9 kernel; key 3: L2 prefetch of the input (1 = separate kernel,
+ * d+1 = in-kernel, d blocks ahead); key 10: 1 = warp-per-column stages in the row pass; key 11: 1 = TMA tile store in the
+ * 12 x 12 x 9 kernel; key 12: S = forward transform in sub-batches of S blocks on two internal streams. */
 int kgpu_set_tuning(int key, int value);
 
 /* Diagnostics: device buffer (6 uint64 per CTA of the cols kernel) receiving globaltimer stamps

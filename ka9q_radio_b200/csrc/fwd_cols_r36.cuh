@@ -11,8 +11,10 @@
 // Twiddles: a thread needs W^{j t}, t = 1..35.  Ten are loaded (t = 1..5 and 6, 12, .., 30), the other 25 are one product
 // each (t = 6a + b): depth 1, so the rounding error stays at one multiply.  Same for the inter-pass factors
 // W_nc^{n2 (t + 36 k')} = A[n2][t] * (W_nc^{36 n2})^{k'}.
-// Shared-memory layout: a column is 36 blocks of 36 points padded to 37, column pitch = 2 mod 16: stage 0's stores
-// (8 columns x 2 consecutive j) and stage 1's loads (8 columns x 2 consecutive blocks) are both bank-conflict free.
+// Shared-memory layout: a column is 36 blocks of 36 points padded to 38 (V128, default) or 37, column pitch = 2 mod 16:
+// stage 0's stores (8 columns x 2 consecutive j) and stage 1's loads are bank-conflict free either way.
+// Measured (tools/kbench.py, cfg-2, us per block): v2 12x12x9 6.32 -> 36x36 5.62 -> + inter-pass rows padded to 128 B 5.39
+// -> + LDS.128 in stage 1 5.30.
 #pragma once
 #include "static_kernels_v2.cuh"
 
@@ -32,9 +34,11 @@ __device__ __forceinline__ float2 r36_power(float2 const (&wb)[6], float2 const 
   return cmul(wa[a], wb[b]);
 }
 
-template <int FMT, int N2C>
+// V128: blocks padded to 38 (even) so that stage 1 reads its 36 contiguous points with 18 LDS.128 (a quarter-warp = the 8
+// columns of one butterfly: 8 x 16 B at a column pitch of 4 banks = all 32 banks once) instead of 36 LDS.64.
+template <int FMT, int N2C, bool V128 = true>
 __global__ void __launch_bounds__(288, 2) fwd_cols_r36(Pass1Args const a, ColsR36Tables const tb) {
-  constexpr int R = 36, BLK = 37, CP = 1346, T = 288;  // 36 * 37 = 1332 <= 1346, 1346 = 2 mod 16
+  constexpr int R = 36, BLK = V128 ? 38 : 37, CP = V128 ? 1378 : 1346, T = 288;  // 36 * BLK <= CP, CP = 2 mod 16
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float2 *tile = reinterpret_cast<float2 *>(smem_raw);  // [8][CP]
   float2 *s_tw0 = tile + 8 * CP;                        // [10][36]
@@ -43,8 +47,10 @@ __global__ void __launch_bounds__(288, 2) fwd_cols_r36(Pass1Args const a, ColsR3
   int const tid = threadIdx.x;
   int const c = tid & 7, ul = tid >> 3;  // column of the tile, butterfly 0..35
   int const c0 = blockIdx.x * 8, blk = blockIdx.y;
-  constexpr int n2 = N2C;
-  constexpr long nc = 1296L * N2C;
+  int const n2 = N2C ? N2C : a.n2;  // N2C: number of columns as a compile-time constant (0 = from the arguments)
+  // rows of the inter-pass buffer padded to whole 128-byte lines: every 64-byte store piece of this kernel then lies in ONE
+  // line (with the natural pitch of 10 000 bytes 3 of 8 pieces straddle two: +27 % L1TEX wavefronts for the stores)
+  int const ld = N2C ? (N2C + 15) / 16 * 16 : a.mid_ld;
   int const ncols = min(8, n2 - c0);
   bool const col_ok = c < ncols;
   int const n2g = c0 + c;
@@ -122,8 +128,18 @@ __global__ void __launch_bounds__(288, 2) fwd_cols_r36(Pass1Args const a, ColsR3
   if (col_ok) {
     float2 x[R];
     float2 const *p = mycol + ul * BLK;
+    if (V128) {
+      float4 const *p4 = reinterpret_cast<float4 const *>(p);
 #pragma unroll
-    for (int m = 0; m < R; m++) x[m] = p[m];
+      for (int m = 0; m < R / 2; m++) {
+        float4 const v = p4[m];
+        x[2 * m] = make_float2(v.x, v.y);
+        x[2 * m + 1] = make_float2(v.z, v.w);
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < R; m++) x[m] = p[m];
+    }
     Dft<R, false>::run(x);
     float2 wb[6], wa[6];
 #pragma unroll
@@ -132,10 +148,10 @@ __global__ void __launch_bounds__(288, 2) fwd_cols_r36(Pass1Args const a, ColsR3
       wa[b] = s_twB[c * 10 + (4 + b)];
     }
     float2 const w0 = make_float2(twA.x * a.out_scale, twA.y * a.out_scale);
-    float2 *dst = a.mid + (long)blk * nc + n2g + (long)ul * n2;
+    float2 *dst = a.mid + (long)blk * 1296 * ld + n2g + (long)ul * ld;
     dst[0] = cmul(x[0], w0);
 #pragma unroll
-    for (int k = 1; k < R; k++) dst[(long)(R * k) * n2] = cmul(x[k], cmul(w0, r36_power(wb, wa, k)));
+    for (int k = 1; k < R; k++) dst[(long)(R * k) * ld] = cmul(x[k], cmul(w0, r36_power(wb, wa, k)));
   }
   (void)T;
 }

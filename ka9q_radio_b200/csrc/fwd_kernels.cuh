@@ -42,6 +42,7 @@ struct Pass1Args {
   float out_scale;      // v2 kernels: factor folded into the inter-pass twiddle (int16 scale, x0.5 when the split is pre-halved)
   int pf_dist;          // blocks of look-ahead for the in-kernel L2 prefetch of the input stream (0 = off)
   int mid_mod;          // experiment (tuning 7): alias the inter-pass buffer of block b onto b % mid_mod (0 = off)
+  int mid_ld;           // elements between consecutive k1 rows of `mid` (>= n2; the 36 x 36 kernel pads rows to 128 bytes)
 };
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
@@ -194,6 +195,7 @@ struct Pass2Args {
   long spec_stride;
   unsigned long long *dbg;  // or nullptr: per-CTA phase timestamps
   int mid_mod;          // see Pass1Args
+  int mid_ld;           // see Pass1Args
 };
 
 __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_kernel(Pass2Args const a) {

@@ -543,9 +543,13 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
         set_smem((const void *)fwd_cols_v2<2, 1250, 0, true>, sv1 + 128) ||
         set_smem((const void *)fwd_cols_v2<1, 1250, 0, false, 16>, sizeof(float2) * (16 * 1297 + 1288 + 160)) ||
         set_smem((const void *)fwd_cols_v2<1, 1250, 0, false, 6>, sizeof(float2) * (6 * 1298 + 1288 + 60)) ||
-        set_smem((const void *)fwd_cols_r36<0, 1250>, sizeof(float2) * (8 * 1346 + 440)) ||
-        set_smem((const void *)fwd_cols_r36<1, 1250>, sizeof(float2) * (8 * 1346 + 440)) ||
-        set_smem((const void *)fwd_cols_r36<2, 1250>, sizeof(float2) * (8 * 1346 + 440)) ||
+        set_smem((const void *)fwd_cols_r36<0, 1250>, sizeof(float2) * (8 * 1378 + 440)) ||
+        set_smem((const void *)fwd_cols_r36<1, 1250>, sizeof(float2) * (8 * 1378 + 440)) ||
+        set_smem((const void *)fwd_cols_r36<2, 1250>, sizeof(float2) * (8 * 1378 + 440)) ||
+        set_smem((const void *)fwd_cols_r36<0, 0>, sizeof(float2) * (8 * 1378 + 440)) ||
+        set_smem((const void *)fwd_cols_r36<1, 0>, sizeof(float2) * (8 * 1378 + 440)) ||
+        set_smem((const void *)fwd_cols_r36<2, 0>, sizeof(float2) * (8 * 1378 + 440)) ||
+        set_smem((const void *)fwd_rows_v2<true, 1296, true, false, 2>, sv2) || set_smem((const void *)fwd_rows_v2<true, 1296, true, false, 4>, sv2) ||
         set_smem((const void *)fwd_rows_v2<false, 1296, false>, sv2)) {
       kgpu_master_destroy(m);
       return nullptr;
@@ -643,6 +647,7 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
   a1.stats = (fmt == KGPU_FMT_I16) ? (IngestStats *)d_stats : nullptr;
   a1.dbg = (unsigned long long *)g_dbg_buf;
   a1.mid_mod = 0;
+  a1.mid_ld = m->sp.n2;
   a1.pf_dist = g_tuning[3].load() >= 2 ? g_tuning[3].load() - 1 : 0;
   dim3 const g1((unsigned)((m->sp.n2 + kTile - 1) / kTile), (unsigned)nblocks);
   if (g_tuning[3].load() == 1) {  // experiment: pull the input windows into L2 with coalesced requests first
@@ -671,15 +676,22 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
         if (f == 0) fwd_cols_v2<0, 1250, 0, true><<<g1, 288, sv1 + 128, st>>>(a1, t2, m->mid_map);
         else if (f == 1) fwd_cols_v2<1, 1250, 0, true><<<g1, 288, sv1 + 128, st>>>(a1, t2, m->mid_map);
         else fwd_cols_v2<2, 1250, 0, true><<<g1, 288, sv1 + 128, st>>>(a1, t2, m->mid_map);
-      } else if (m->sp.n2 == 1250 && g_tuning[13].load() == 3) {  // two fat stages (36 x 36), one trip through shared memory
-        size_t const sr = sizeof(float2) * (8 * 1346 + 440);
+      } else if (g_tuning[13].load() == 0) {  // default: two fat stages (36 x 36), one trip through shared memory
+        if (m->sp.n2 == 1250 && m->static_rows == 1250) a1.mid_ld = (m->sp.n2 + 15) / 16 * 16;  // rows padded to 128 B (both kernels know)
+        size_t const sr = sizeof(float2) * (8 * 1378 + 440);
         ColsR36Tables t3;
         t3.tw0 = m->d_r36_tw0;
         t3.twA = m->d_r36_A;
         t3.twB = m->d_r36_B;
-        if (f == 0) fwd_cols_r36<0, 1250><<<g1, 288, sr, st>>>(a1, t3);
-        else if (f == 1) fwd_cols_r36<1, 1250><<<g1, 288, sr, st>>>(a1, t3);
-        else fwd_cols_r36<2, 1250><<<g1, 288, sr, st>>>(a1, t3);
+        if (m->sp.n2 == 1250 && m->static_rows == 1250) {
+          if (f == 0) fwd_cols_r36<0, 1250><<<g1, 288, sr, st>>>(a1, t3);
+          else if (f == 1) fwd_cols_r36<1, 1250><<<g1, 288, sr, st>>>(a1, t3);
+          else fwd_cols_r36<2, 1250><<<g1, 288, sr, st>>>(a1, t3);
+        } else {
+          if (f == 0) fwd_cols_r36<0, 0><<<g1, 288, sr, st>>>(a1, t3);
+          else if (f == 1) fwd_cols_r36<1, 0><<<g1, 288, sr, st>>>(a1, t3);
+          else fwd_cols_r36<2, 0><<<g1, 288, sr, st>>>(a1, t3);
+        }
       } else if (m->sp.n2 == 1250 && f == 1 && g_tuning[13].load() == 2) {  // 6-column tiles, three CTAs per SM
         size_t const sv6 = sizeof(float2) * (6 * 1298 + 1288 + 60);
         dim3 const g6((unsigned)((m->sp.n2 + 5) / 6), (unsigned)nblocks);
@@ -719,12 +731,15 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
   a2.spec_stride = m->spec_stride;
   a2.dbg = g_dbg_buf2 ? (unsigned long long *)g_dbg_buf2 : nullptr;
   a2.mid_mod = 0;
+  a2.mid_ld = a1.mid_ld;
   dim3 const g2((unsigned)m->n_item_ctas, (unsigned)nblocks);
   {
     ProfScope ps(K_FWD_ROWS, st);
     if (use_static && m->static_rows == 1250) {
       size_t const sv2 = sizeof(float2) * (8 * 1250 + 1246);
-      if (a2.real_split && halved && g_tuning[10].load() == 1) fwd_rows_v2<true, 1296, true, true><<<g2, 256, sv2, st>>>(a2, tb);
+      if (a2.real_split && halved && g_tuning[10].load() == 2) fwd_rows_v2<true, 1296, true, false, 2><<<g2, 256, sv2, st>>>(a2, tb);
+      else if (a2.real_split && halved && g_tuning[10].load() == 4) fwd_rows_v2<true, 1296, true, false, 4><<<g2, 256, sv2, st>>>(a2, tb);
+      else if (a2.real_split && halved && g_tuning[10].load() == 1) fwd_rows_v2<true, 1296, true, true><<<g2, 256, sv2, st>>>(a2, tb);
       else if (a2.real_split && halved) fwd_rows_v2<true, 1296, true><<<g2, 256, sv2, st>>>(a2, tb);
       else if (a2.real_split) fwd_rows_v2<true><<<g2, 256, sv2, st>>>(a2, tb);
       else if (m->sp.n1 == 1296) fwd_rows_v2<false, 1296, false><<<g2, 256, sv2, st>>>(a2, tb);
@@ -746,7 +761,7 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
     cudaFree(m->d_mid);
     m->d_mid = nullptr;
     m->mid_blocks = 0;
-    CUDA_OK(cudaMalloc(&m->d_mid, sizeof(float2) * (size_t)m->nc * (size_t)nblocks));
+    CUDA_OK(cudaMalloc(&m->d_mid, sizeof(float2) * (size_t)m->sp.n1 * (size_t)((m->sp.n2 + 15) / 16 * 16) * (size_t)nblocks));
     m->mid_blocks = nblocks;
     m->mid_map_ok = (m->static_cols == 1296) && encode_mid_map(m);
   }
@@ -773,7 +788,7 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
     int const rc = forward_span(m, (char const *)d_in + (size_t)b0 * in_bytes_per_block, fmt, scale, derandomize, nb,
                                 (float2 *)d_spec + (size_t)b0 * (size_t)m->spec_stride,
                                 d_stats ? (void *)((IngestStats *)d_stats + b0) : nullptr, m->aux[s & 1],
-                                m->d_mid + (size_t)(s & 1) * (size_t)sub * (size_t)m->nc);
+                                m->d_mid + (size_t)(s & 1) * (size_t)sub * (size_t)m->sp.n1 * (size_t)((m->sp.n2 + 15) / 16 * 16));
     if (rc) return rc;
   }
   for (int i = 0; i < 2; i++) {

@@ -5,9 +5,9 @@ for spec in "$@"; do
   port=$((port+1))
   IFS=: read mode blocks depth <<< "$spec"
   blocks=${blocks:-32}; depth=${depth:-2}
-  tag=${mode}_b${blocks}_d${depth}
+  tag=${mode}_b${blocks}_d${depth}${MG_TAG}
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port \
-      bench.py --gpus $N --steps 10 --warmup 3 --mg-mode $mode --blocks-per-step $blocks --depth $depth > gpurun_out/scale_${N}_${tag}.log 2>&1
+      bench.py --gpus $N --steps 10 --warmup 3 --mg-mode $mode --blocks-per-step $blocks --depth $depth $MG_EXTRA > gpurun_out/scale_${N}_${tag}.log 2>&1
   echo "== $tag rc=$?"
   grep '^{' gpurun_out/scale_${N}_${tag}.log | tail -1 > gpurun_out/scale_${N}_${tag}.json
   python - <<PY
