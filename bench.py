@@ -355,6 +355,41 @@ def run_ours(args) -> None:
                                    broadcast=lambda slot: dist.all_gather_into_tensor(
                                        spec2[slot].view(-1), spec2[slot][rank * Bq:(rank + 1) * Bq].reshape(-1), async_op=True))
         par = (f"{world} GPUs: every rank transforms {Bq} of the step's {B} blocks, 1 NCCL all-gather of the spectra per step")
+    elif mode == "a2a":
+        # block-parallel forward + slice hand-off: every rank transforms 1/world of the step's blocks and sends each peer only
+        # the bins that peer's channels read (ONE all-to-all per step; cfg-5: 7 x 6 MB out of every rank instead of 363 MB in)
+        if B % world:
+            raise SystemExit("--mg-mode a2a needs blocks-per-step divisible by the number of GPUs")
+        Bq = B // world
+        from ka9q_radio_b200 import workloads
+        lo_hi = []
+        for r in range(world):
+            wr = workloads.by_name(w.name, r, world)
+            lo = max(0, min(abs(c.shift) for c in wr.channels) - 304) // 4 * 4
+            lo_hi.append((lo, min(cz.master.bins, max(abs(c.shift) for c in wr.channels) + 304)))
+        width = max(hi - lo for lo, hi in lo_hi)
+        a_send = [torch.zeros((world, Bq, width), dtype=torch.complex64, device=dev) for _ in range(nslots)]
+        a_recv = [torch.empty((world, Bq, width), dtype=torch.complex64, device=dev) for _ in range(nslots)]
+
+        def fwd_part(step, slot):
+            mine = spec2[slot][rank * Bq:(rank + 1) * Bq]
+            cz.forward(d_stream, Bq, mine, scale=w.scale, first_block=(step % ngroups) * B + rank * Bq)
+            for q in range(world):
+                lo, hi = lo_hi[q]
+                a_send[slot][q, :, : hi - lo].copy_(mine[:, lo:hi])
+
+        def exchange(slot):
+            h = dist.all_to_all_single(a_recv[slot].view(-1), a_send[slot].view(-1), async_op=True)
+            lo, hi = lo_hi[rank]
+
+            def unpack():
+                for p in range(world):
+                    spec2[slot][p * Bq:(p + 1) * Bq, lo:hi].copy_(a_recv[slot][p, :, : hi - lo])
+            return _Multi([h], then=unpack)
+
+        sharder = PipelinedSharder(rank, world, forward=fwd_part, channels=chan, depth=nslots, forward_on_all=True, broadcast=exchange)
+        par = (f"{world} GPUs: every rank transforms {Bq} of the step's {B} blocks and sends each peer only the bins its channels "
+               f"read ({(lo_hi[0][1] - lo_hi[0][0]) * 8 / 1e6:.2f} MB of {cz.master.bins * 8 / 1e6:.2f} MB per block), 1 NCCL all-to-all per step")
     elif mode == "slices":
         # slice hand-off: rank r only receives the bins its own channels read (cfg-5: 1024 x 188 + 600 bins of 1 620 001)
         lo_hi = [None] * world
@@ -485,7 +520,7 @@ def run_ours(args) -> None:
         peaks = json.loads(pk.read_text())
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback, B200_PROFILING.md)"
-    blocks_fwd = B // world if mode == "allgather" else B
+    blocks_fwd = B // world if mode in ("allgather", "a2a") else B
     alg_per_kernel = {"fwd_cols": alg_fwd_in * blocks_fwd, "fwd_rows": alg_fwd_out * blocks_fwd, "chan": alg_chan * B}
     kernels = {}
     for name, (tot_ms, cnt) in prof.items():
@@ -713,12 +748,13 @@ def main():
     ap.add_argument("--filter-h-blocks-per-write", type=int, default=2)
     ap.add_argument("--quick", action="store_true", help="sweeps: skip the parity self-check and the e2e legs")
     ap.add_argument("--depth", type=int, default=2, help="spectrum ring depth of the multi-GPU pipeline")
-    ap.add_argument("--mg-mode", default="allgather", choices=["spectrum", "spectrum-mc", "input", "allgather", "slices"],
+    ap.add_argument("--mg-mode", default="allgather", choices=["spectrum", "spectrum-mc", "input", "allgather", "slices", "a2a"],
                     help="multi-GPU hand-off of the shared forward spectrum, one NCCL collective per step: `allgather` (default) = every "
                          "rank transforms 1/N of the step's blocks and each block's spectrum is broadcast once by the rank that made it; "
                          "`spectrum` = all blocks transformed on rank 0 + one ncclBroadcast (north_star's literal form: rank 0's NVLink "
                          "egress and HBM bound it); `spectrum-mc` = the same through this repository's NVSwitch-multicast copy kernel; "
-                         "`input` = broadcast of the raw window, forward replicated; `slices` = per-rank bin slices (send/recv)")
+                         "`input` = broadcast of the raw window, forward replicated; `slices` = rank 0 scatters per-rank bin slices; "
+                         "`a2a` = block-parallel forward + all-to-all of per-rank bin slices")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -101,6 +101,8 @@ int kgpu_bank_define_ex(kgpu_bank *b, int idx, int olen, int out_type);
 /* set_filter (filter.c:968-1045): Kaiser-windowed sinc designed on the host in double, forward
  * transformed on the device.  low/high are fractions of the output rate. */
 int kgpu_bank_set_filter(kgpu_bank *b, int idx, double low, double high, double kaiser_beta);
+/* Same, synchronising only `stream` (on which the caller orders every launch that reads this bank) instead of the device. */
+int kgpu_bank_set_filter_on(kgpu_bank *b, int idx, double low, double high, double kaiser_beta, void *stream);
 /* Caller-supplied frequency response (points complex floats), e.g. for tests. */
 int kgpu_bank_set_response(kgpu_bank *b, int idx, float const *response);
 int kgpu_bank_get_response(kgpu_bank *b, int idx, float *response); /* device -> host copy */
@@ -158,7 +160,8 @@ int kgpu_use_static_kernels(int on);
 /* Experiment knobs for A/B measurements (0 = shipped default everywhere).  key 13: column pass of the 1296 x n2
  * transform: 0 = 36 x 36 two-stage kernel (default), 4 = round-1 12 x 12 x 9 kernel, 1 / 2 = that kernel with 16 / 6-column tiles;
  * key 2: 1 / 2 = table twiddles / I2F unpack in the 12 x 12 x 9 kernel; key 3: L2 prefetch of the input (1 = separate kernel,
- * d+1 = in-kernel, d blocks ahead); key 10: 1 = warp-per-column stages in the row pass; key 11: 1 = TMA tile store in the
+ * d+1 = in-kernel, d blocks ahead); key 6: 1 = channel kernel's stage-0 twiddles by products; key 10: row pass: 1 = warp-per-column
+ * stages, 2 / 4 = stage-0 butterflies in groups, 3 = stage-0 twiddles by loads, 5 = stage-1 twiddles by products; key 11: 1 = TMA tile store in the
  * 12 x 12 x 9 kernel; key 12: S = forward transform in sub-batches of S blocks on two internal streams. */
 int kgpu_set_tuning(int key, int value);
 

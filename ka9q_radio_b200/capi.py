@@ -62,6 +62,7 @@ def load() -> C.CDLL:
     L.kgpu_bank_destroy.argtypes = [vp]
     L.kgpu_bank_define.argtypes = [vp, i, i]
     L.kgpu_bank_set_filter.argtypes = [vp, i, d, d, d]
+    L.kgpu_bank_set_filter_on.argtypes = [vp, i, d, d, d, vp]
     L.kgpu_bank_set_response.argtypes = [vp, i, vp]
     L.kgpu_bank_get_response.argtypes = [vp, i, vp]
     L.kgpu_bank_set_shift.argtypes = [vp, i, i]

@@ -991,8 +991,9 @@ int set_filter(struct filter_out *const slave, double low, double high, double c
   if (!host)
     return -1;
   pthread_mutex_lock(&c->mu);
-  cudaStreamSynchronize(c->st);
-  int rc = kgpu_bank_set_filter(c->bank, sc->idx, low, high, kaiser_beta);
+  /* only this master's pipeline stream is synchronised: a retune of one channel must not stall other masters
+   * (filter2 / wfm composite masters of other channel threads) the way a device-wide synchronisation would */
+  int rc = kgpu_bank_set_filter_on(c->bank, sc->idx, low, high, kaiser_beta, c->st);
   if (rc == 0)
     rc = kgpu_bank_get_response(c->bank, sc->idx, (float *)host) > 0 ? 0 : -1;
   if (rc == 0)

@@ -549,6 +549,7 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
         set_smem((const void *)fwd_cols_r36<0, 0>, sizeof(float2) * (8 * 1378 + 440)) ||
         set_smem((const void *)fwd_cols_r36<1, 0>, sizeof(float2) * (8 * 1378 + 440)) ||
         set_smem((const void *)fwd_cols_r36<2, 0>, sizeof(float2) * (8 * 1378 + 440)) ||
+        set_smem((const void *)fwd_rows_v2<true, 1296, true, false, 0, false>, sv2) || set_smem((const void *)fwd_rows_v2<true, 1296, true, false, 0, true, true>, sv2) ||
         set_smem((const void *)fwd_rows_v2<true, 1296, true, false, 2>, sv2) || set_smem((const void *)fwd_rows_v2<true, 1296, true, false, 4>, sv2) ||
         set_smem((const void *)fwd_rows_v2<false, 1296, false>, sv2)) {
       kgpu_master_destroy(m);
@@ -737,7 +738,9 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
     ProfScope ps(K_FWD_ROWS, st);
     if (use_static && m->static_rows == 1250) {
       size_t const sv2 = sizeof(float2) * (8 * 1250 + 1246);
-      if (a2.real_split && halved && g_tuning[10].load() == 2) fwd_rows_v2<true, 1296, true, false, 2><<<g2, 256, sv2, st>>>(a2, tb);
+      if (a2.real_split && halved && g_tuning[10].load() == 3) fwd_rows_v2<true, 1296, true, false, 0, false><<<g2, 256, sv2, st>>>(a2, tb);  // A/B: stage-0 twiddles by loads
+      else if (a2.real_split && halved && g_tuning[10].load() == 5) fwd_rows_v2<true, 1296, true, false, 0, true, true><<<g2, 256, sv2, st>>>(a2, tb);  // A/B: stage-1 twiddles by products
+      else if (a2.real_split && halved && g_tuning[10].load() == 2) fwd_rows_v2<true, 1296, true, false, 2><<<g2, 256, sv2, st>>>(a2, tb);
       else if (a2.real_split && halved && g_tuning[10].load() == 4) fwd_rows_v2<true, 1296, true, false, 4><<<g2, 256, sv2, st>>>(a2, tb);
       else if (a2.real_split && halved && g_tuning[10].load() == 1) fwd_rows_v2<true, 1296, true, true><<<g2, 256, sv2, st>>>(a2, tb);
       else if (a2.real_split && halved) fwd_rows_v2<true, 1296, true><<<g2, 256, sv2, st>>>(a2, tb);
@@ -910,7 +913,7 @@ struct ChanHost {
   bool defined = false, enabled = false, has_response = false;
   bool real_out = false;  // REAL-output slave (filter.c:370-390): olen floats per block
   int olen = 0, points = 0, plan = -1, shift = 0, flags = 0;
-  long resp_off = 0;
+  long resp_off = 0, resp_cap = 0;  // region of the response arena owned by this slot
   ChanAux aux{};          // oscillator / beam parameters (zero = unused)
 };
 struct kgpu_bank {
@@ -1118,7 +1121,9 @@ static int bank_define(kgpu_bank *b, int idx, int olen, bool real_out) {
   c.real_out = real_out;
   if (!(c.defined && c.points == points)) {
     long const need = (points + 3) / 4 * 4;
-    if (b->resp_used + need > b->resp_cap) {
+    if (need <= c.resp_cap) {
+      // the slot's old region is large enough: reuse it (a long-running radiod re-creates channels at other rates)
+    } else if (b->resp_used + need > b->resp_cap) {
       long const ncap = std::max<long>(2 * b->resp_cap, b->resp_used + std::max<long>(need, 64L * 1024));
       float2 *nb = nullptr;
       CUDA_OK(cudaMalloc(&nb, sizeof(float2) * (size_t)ncap));
@@ -1129,8 +1134,11 @@ static int bank_define(kgpu_bank *b, int idx, int olen, bool real_out) {
       b->d_resp = nb;
       b->resp_cap = ncap;
     }
-    c.resp_off = b->resp_used;
-    b->resp_used += need;
+    if (need > c.resp_cap) {
+      c.resp_off = b->resp_used;
+      c.resp_cap = need;
+      b->resp_used += need;
+    }
     c.has_response = false;
   }
   c.defined = true;
@@ -1143,26 +1151,38 @@ static int bank_define(kgpu_bank *b, int idx, int olen, bool real_out) {
   return points;
 }
 
-static int upload_taps_and_transform(kgpu_bank *b, ChanHost &c, float2 const *host, bool transform) {
+// st == nullptr: legacy entry points, whole-device synchronisation (any stream may be using the response);
+// otherwise only `st` is synchronised: the caller guarantees that every launch reading this bank is ordered on it
+static int upload_taps_and_transform(kgpu_bank *b, ChanHost &c, float2 const *host, bool transform, cudaStream_t st = nullptr,
+                                     bool on_stream = false) {
   float2 *dst = b->d_resp + c.resp_off;
   // the response may be in use by a queued run: wait, then swap (the reference takes
   // response_mutex for the same reason, filter.c:1039-1043)
-  CUDA_OK(cudaDeviceSynchronize());
-  CUDA_OK(cudaMemcpy(dst, host, sizeof(float2) * (size_t)c.points, cudaMemcpyHostToDevice));
+  if (on_stream) CUDA_OK(cudaStreamSynchronize(st));
+  else CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaMemcpyAsync(dst, host, sizeof(float2) * (size_t)c.points, cudaMemcpyHostToDevice, st));
   if (transform) {
     size_t const sm = sizeof(float2) * (size_t)c.points;
     if (set_smem((const void *)response_fft_kernel, sm)) return -1;
-    response_fft_kernel<<<1, 32, sm>>>(dst, c.plan);
+    response_fft_kernel<<<1, 32, sm, st>>>(dst, c.plan);
     g_launches++;
     CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaDeviceSynchronize());
   }
+  if (on_stream) CUDA_OK(cudaStreamSynchronize(st));
+  else CUDA_OK(cudaDeviceSynchronize());
   c.has_response = true;
   b->dirty = true;
   return 0;
 }
 
+static int bank_set_filter(kgpu_bank *b, int idx, double low, double high, double kaiser_beta, cudaStream_t st, bool on_stream);
 extern "C" int kgpu_bank_set_filter(kgpu_bank *b, int idx, double low, double high, double kaiser_beta) {
+  return bank_set_filter(b, idx, low, high, kaiser_beta, nullptr, false);
+}
+extern "C" int kgpu_bank_set_filter_on(kgpu_bank *b, int idx, double low, double high, double kaiser_beta, void *stream) {
+  return bank_set_filter(b, idx, low, high, kaiser_beta, (cudaStream_t)stream, true);
+}
+static int bank_set_filter(kgpu_bank *b, int idx, double low, double high, double kaiser_beta, cudaStream_t st, bool on_stream) {
   if (bad_idx(b, idx) || !b->ch[(size_t)idx].defined) return fail("kgpu_bank_set_filter: channel not defined");
   ChanHost &c = b->ch[(size_t)idx];
   std::vector<float2> taps;
@@ -1172,7 +1192,7 @@ extern "C" int kgpu_bank_set_filter(kgpu_bank *b, int idx, double low, double hi
   }
   if (design_taps(c.points, c.olen, b->m->N, b->m->in_type == KGPU_REAL, low, high, kaiser_beta, taps))
     return fail("kgpu_bank_set_filter: rejected (NaN or M < 2), cf. filter.c:969,989");
-  return upload_taps_and_transform(b, c, taps.data(), true);
+  return upload_taps_and_transform(b, c, taps.data(), true, st, on_stream);
 }
 extern "C" int kgpu_bank_set_response(kgpu_bank *b, int idx, float const *response) {
   if (bad_idx(b, idx) || !b->ch[(size_t)idx].defined || !response) return fail("kgpu_bank_set_response: bad arguments");
@@ -1181,7 +1201,7 @@ extern "C" int kgpu_bank_set_response(kgpu_bank *b, int idx, float const *respon
 extern "C" int kgpu_bank_get_response(kgpu_bank *b, int idx, float *response) {
   if (bad_idx(b, idx) || !b->ch[(size_t)idx].has_response || !response) return fail("kgpu_bank_get_response: none");
   ChanHost &c = b->ch[(size_t)idx];
-  CUDA_OK(cudaDeviceSynchronize());
+  // written by a synchronised upload (above) and never modified by kernels: a plain blocking copy is ordered correctly
   CUDA_OK(cudaMemcpy(response, b->d_resp + c.resp_off, sizeof(float2) * (size_t)c.points, cudaMemcpyDeviceToHost));
   return c.points;
 }
@@ -1267,11 +1287,14 @@ template <class P> static int launch_chan_v2(ChanArgs const &a, int n, int nbloc
   size_t const sm = sizeof(float2) * ((size_t)(2 * P::len + 4) * kChanWarps + static_tw_count<P>() + 2);
   static bool attr_done = false;
   if (!attr_done) {
-    if (set_smem((const void *)chan_v2<P, false>, sm) || set_smem((const void *)chan_v2<P, true>, sm)) return -1;
+    if (set_smem((const void *)chan_v2<P, false>, sm) || set_smem((const void *)chan_v2<P, true>, sm) ||
+        set_smem((const void *)chan_v2<P, false, true>, sm))
+      return -1;
     attr_done = true;
   }
   dim3 const g((unsigned)((n + kChanWarps - 1) / kChanWarps), (unsigned)nblocks);
   if (osc) chan_v2<P, true><<<g, kChanWarps * 32, sm, st>>>(a);
+  else if (g_tuning[6].load() == 1) chan_v2<P, false, true><<<g, kChanWarps * 32, sm, st>>>(a);  // A/B: stage-0 twiddles by products
   else chan_v2<P, false><<<g, kChanWarps * 32, sm, st>>>(a);
   return 0;
 }

@@ -355,3 +355,30 @@ def test_tuned_output_noise_and_batch_extensions(oracle, cuda_dev):
             for c in range(24):
                 assert np.abs(outs[c] - ref[b][c]).max() / np.abs(ref[b][c]).max() < TOL, (b, c)
         assert sum(lib.ref_channel_drops(s.h, c) for c in range(24)) == 0
+
+
+@pytest.mark.gpu
+def test_secondary_complex_master_like_filter2(oracle, cuda_dev):
+    """radio.c:1572-1602 / :1503-1514: a channel's output is written into a second, small COMPLEX master (`filter2`) with
+    write_cfilter, run inline by the same thread (perform_inline, owner shortcut filter.c:681-683), and read back with shift 0.
+    Both masters live in the same library at the same time."""
+    lib = _load("driver_gpuhdr.so")
+    L, M, nb = 48000, 12001, 6
+    x = oracle.siggen_real(nb * L, 0.1, 0.02, 0.25, 1.0)
+    ch = dict(olen=480, shift=15000, low=-1 / 3, high=1 / 3, beta=11.0)
+    first, _ = oracle.run_stream(x, L, M, [ch])
+    mid = np.concatenate([first[b][0] for b in range(nb)]).astype(np.complex64)
+    L2, M2 = 480, 97   # blocking = 1: N = 576 = 2^6 * 9
+    ch2 = dict(olen=480, shift=0, low=-0.125, high=0.125, beta=7.0)
+    second, _ = oracle.run_stream(mid, L2, M2, [ch2])
+    with oracle.RefSession(L, M, oracle.KO_REAL, lib=lib) as s1, oracle.RefSession(L2, M2, oracle.KO_COMPLEX, lib=lib) as s2:
+        a = s1.add_channel(480, -1 / 3, 1 / 3, 11.0)
+        b2 = s2.add_channel(480, -0.125, 0.125, 7.0)
+        for b in range(nb):
+            assert s1.write(x[b * L:(b + 1) * L]) == 1
+            y = s1.execute(a, 15000)
+            assert np.abs(y - first[b][0]).max() / np.abs(first[b][0]).max() < TOL
+            assert s2.write(y) == 1
+            z = s2.execute(b2, 0)
+            r = second[b][0]
+            assert np.abs(z - r).max() / np.abs(r).max() < 2 * TOL, b   # two cascaded float32 filters

@@ -2,4 +2,5 @@
 mkdir -p gpurun_out
 timeout 300 python tools/ab_check.py 10=2 10=4 > gpurun_out/ab_r02p.txt 2>&1
 timeout 600 python tools/kbench.py --blocks 32 --iters 10 --rounds 3 default 10=2 10=4 > gpurun_out/kbench_r02p.txt 2>&1
+timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/r02p_pytest.txt 2>&1
 echo done

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python tools/ab_check.py 10=3 > gpurun_out/ab_r02t.txt 2>&1
+timeout 600 python tools/kbench.py --blocks 32 --iters 10 --rounds 3 default 10=3 > gpurun_out/kbench_r02t.txt 2>&1
+echo done
