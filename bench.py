@@ -748,7 +748,7 @@ def main():
     ap.add_argument("--filter-h-blocks-per-write", type=int, default=2)
     ap.add_argument("--quick", action="store_true", help="sweeps: skip the parity self-check and the e2e legs")
     ap.add_argument("--depth", type=int, default=2, help="spectrum ring depth of the multi-GPU pipeline")
-    ap.add_argument("--mg-mode", default="allgather", choices=["spectrum", "spectrum-mc", "input", "allgather", "slices", "a2a"],
+    ap.add_argument("--mg-mode", default="a2a", choices=["spectrum", "spectrum-mc", "input", "allgather", "slices", "a2a"],
                     help="multi-GPU hand-off of the shared forward spectrum, one NCCL collective per step: `allgather` (default) = every "
                          "rank transforms 1/N of the step's blocks and each block's spectrum is broadcast once by the rank that made it; "
                          "`spectrum` = all blocks transformed on rank 0 + one ncclBroadcast (north_star's literal form: rank 0's NVLink "

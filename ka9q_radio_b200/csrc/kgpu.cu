@@ -21,6 +21,7 @@
 #include "static_kernels.cuh"
 #include "static_kernels_v2.cuh"
 #include "fwd_cols_r36.cuh"
+#include "fwd_2s.cuh"
 
 using namespace kfft;
 
@@ -410,6 +411,8 @@ struct kgpu_master {
   float2 *d_twU = nullptr, *d_twT = nullptr;                      // v2 cols kernel (1296 columns)
   float2 *d_r36_tw0 = nullptr, *d_r36_A = nullptr, *d_r36_B = nullptr;  // 36 x 36 cols kernel
   int static_cols = 0, static_rows = 0;  // which specialised kernels apply (0 = generic)
+  int static_2s = 0;                     // 1: COMPLEX 800 x 625 on the two-fat-stage kernels of fwd_2s.cuh
+  float2 *d_2s_tw0 = nullptr, *d_2s_A = nullptr, *d_2s_B = nullptr, *d_2s_rtw0 = nullptr;
   float2 *d_mid = nullptr;
   int mid_blocks = 0;
   cudaStream_t aux[2] = {nullptr, nullptr};   // internal streams of the sub-batched forward (tuning 12)
@@ -530,6 +533,33 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
       CUDA_OKP(cudaMemcpy(m->d_r36_A, tA36.data(), sizeof(float2) * tA36.size(), cudaMemcpyHostToDevice));
       CUDA_OKP(cudaMemcpy(m->d_r36_B, tB10.data(), sizeof(float2) * tB10.size(), cudaMemcpyHostToDevice));
     }
+    if (in_type == KGPU_COMPLEX && n1 == 800 && n2 == 625) {  // cfg-4: (25 x 32) x (25 x 25), fwd_2s.cuh
+      using CS = Cols2sShape<25, 32>;
+      using RS = Rows2sShape<25, 25>;
+      constexpr int RA = 25, RB = 32, RC = 25, RD = 25;
+      std::vector<float2> t0((size_t)CS::TW0, make_float2(0.f, 0.f)), tA((size_t)n2 * RA),
+          tB((size_t)(n2 + 8) * CS::NP1, make_float2(0.f, 0.f)), r0((size_t)RS::TW0, make_float2(0.f, 0.f));
+      for (int e = 0; e < CS::NP0; e++)
+        for (int j = 0; j < RB; j++) t0[(size_t)e * RB + j] = root((long)j * Pow<RA>::exponent(e), n1);
+      for (long c = 0; c < n2; c++) {
+        for (int t = 0; t < RA; t++) tA[(size_t)c * RA + t] = root(c * t, m->nc);
+        for (int e = 0; e < CS::NP1; e++) tB[(size_t)c * CS::NP1 + e] = root(c * RA * Pow<RB>::exponent(e), m->nc);
+      }
+      for (int e = 0; e < RS::NP0; e++)
+        for (int j = 0; j < RD; j++) r0[(size_t)e * RD + j] = root((long)j * Pow<RC>::exponent(e), n2);
+      auto up = [](float2 **d, std::vector<float2> const &v) {
+        if (cudaMalloc(d, sizeof(float2) * v.size()) != cudaSuccess) return 1;
+        return cudaMemcpy(*d, v.data(), sizeof(float2) * v.size(), cudaMemcpyHostToDevice) != cudaSuccess ? 1 : 0;
+      };
+      if (up(&m->d_2s_tw0, t0) || up(&m->d_2s_A, tA) || up(&m->d_2s_B, tB) || up(&m->d_2s_rtw0, r0) ||
+          set_smem((const void *)fwd_cols_2s<0, 25, 32>, CS::smem) || set_smem((const void *)fwd_cols_2s<1, 25, 32>, CS::smem) ||
+          set_smem((const void *)fwd_cols_2s<2, 25, 32>, CS::smem) || set_smem((const void *)fwd_rows_2s<25, 25>, RS::smem)) {
+        fail("kgpu_master_create: tables of the 800 x 625 kernels: %s", cudaGetErrorString(cudaGetLastError()));
+        kgpu_master_destroy(m);
+        return nullptr;
+      }
+      m->static_2s = 1;
+    }
     CUDA_OKP(cudaMalloc(&m->d_rootC, sizeof(float2) * tC.size()));
     CUDA_OKP(cudaMemcpy(m->d_rootC, tC.data(), sizeof(float2) * tC.size(), cudaMemcpyHostToDevice));
     size_t const sv1 = sizeof(float2) * (8 * 1298 + 1288 + 80), sv2 = sizeof(float2) * (8 * 1250 + 1246);
@@ -573,6 +603,10 @@ extern "C" void kgpu_master_destroy(kgpu_master *m) {
   cudaFree(m->d_r36_tw0);
   cudaFree(m->d_r36_A);
   cudaFree(m->d_r36_B);
+  cudaFree(m->d_2s_tw0);
+  cudaFree(m->d_2s_A);
+  cudaFree(m->d_2s_B);
+  cudaFree(m->d_2s_rtw0);
   cudaFree(m->d_twT);
   cudaFree(m->d_mid);
   cudaFree(m->d_notch);
@@ -594,10 +628,15 @@ extern "C" int kgpu_master_describe(kgpu_master const *m, char *buf, int buflen)
            m->in_type == KGPU_REAL ? "real" : "complex", m->nc, m->sp.n1, m->sp.n2);
   s += tmp;
   TilePlan const *p1 = host_tile_plan(m->plan1), *p2 = host_tile_plan(m->plan2);
-  for (int i = 0; i < p1->nstages; i++) s += std::to_string(p1->radix[i]) + (i + 1 < p1->nstages ? "," : "");
+  if (m->static_2s) s += "25,32";
+  else if (m->static_cols == 1296) s += "36,36";  // fwd_cols_r36 (the tile plan is what the generic kernels would run)
+  else
+    for (int i = 0; i < p1->nstages; i++) s += std::to_string(p1->radix[i]) + (i + 1 < p1->nstages ? "," : "");
   s += "] rows radices [";
   for (int i = 0; i < p2->nstages; i++) s += std::to_string(p2->radix[i]) + (i + 1 < p2->nstages ? "," : "");
-  snprintf(tmp, sizeof tmp, "]; smem %zu/%zu B; grids %d/%d CTAs per block", m->smem1, m->smem2,
+  snprintf(tmp, sizeof tmp, "]; smem %zu/%zu B; grids %d/%d CTAs per block",
+           m->static_2s ? Cols2sShape<25, 32>::smem : m->static_cols == 1296 ? sizeof(float2) * (8 * 1378 + 440) : m->smem1,
+           m->static_2s ? Rows2sShape<25, 25>::smem : m->smem2,
            (m->sp.n2 + kTile - 1) / kTile, m->n_item_ctas);
   s += tmp;
   snprintf(buf, (size_t)buflen, "%s", s.c_str());
@@ -663,7 +702,19 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
   bool halved = false;
   {
     ProfScope ps(K_FWD_COLS, st);
-    if (use_static && m->static_cols == 1296) {
+    if (use_static && m->static_2s) {
+      int const f = (fmt != KGPU_FMT_I16) ? 0 : ((derandomize || a1.stats) ? 2 : 1);
+      using CS = Cols2sShape<25, 32>;
+      Cols2sTables t4;
+      t4.tw0 = m->d_2s_tw0;
+      t4.twA = m->d_2s_A;
+      t4.twB = m->d_2s_B;
+      a1.out_scale = (fmt == KGPU_FMT_I16) ? scale : 1.0f;
+      a1.mid_ld = (m->sp.n2 + 15) / 16 * 16;
+      if (f == 0) fwd_cols_2s<0, 25, 32><<<g1, CS::T, CS::smem, st>>>(a1, t4);
+      else if (f == 1) fwd_cols_2s<1, 25, 32><<<g1, CS::T, CS::smem, st>>>(a1, t4);
+      else fwd_cols_2s<2, 25, 32><<<g1, CS::T, CS::smem, st>>>(a1, t4);
+    } else if (use_static && m->static_cols == 1296) {
       int const f = (fmt != KGPU_FMT_I16) ? 0 : ((derandomize || a1.stats) ? 2 : 1);
       size_t const sv1 = sizeof(float2) * (8 * 1298 + 1288 + 80);
       ColsV2Tables t2;
@@ -736,7 +787,11 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
   dim3 const g2((unsigned)m->n_item_ctas, (unsigned)nblocks);
   {
     ProfScope ps(K_FWD_ROWS, st);
-    if (use_static && m->static_rows == 1250) {
+    if (use_static && m->static_2s) {
+      using RS = Rows2sShape<25, 25>;
+      dim3 const g2s((unsigned)((m->sp.n1 + 7) / 8), (unsigned)nblocks);
+      fwd_rows_2s<25, 25><<<g2s, RS::T, RS::smem, st>>>(a2, m->d_2s_rtw0);
+    } else if (use_static && m->static_rows == 1250) {
       size_t const sv2 = sizeof(float2) * (8 * 1250 + 1246);
       if (a2.real_split && halved && g_tuning[10].load() == 3) fwd_rows_v2<true, 1296, true, false, 0, false><<<g2, 256, sv2, st>>>(a2, tb);  // A/B: stage-0 twiddles by loads
       else if (a2.real_split && halved && g_tuning[10].load() == 5) fwd_rows_v2<true, 1296, true, false, 0, true, true><<<g2, 256, sv2, st>>>(a2, tb);  // A/B: stage-1 twiddles by products

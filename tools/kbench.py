@@ -10,7 +10,6 @@ import numpy as np, torch
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from ka9q_radio_b200 import workloads
-W = workloads.cfg2()
 from ka9q_radio_b200 import capi
 from ka9q_radio_b200.channelizer import Channelizer
 
@@ -18,18 +17,23 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--blocks", type=int, default=8)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--rounds", type=int, default=3)
-ap.add_argument("--nchan", type=int, default=1024)
+ap.add_argument("--nchan", type=int, default=0, help="0 = the workload's own channel list")
+ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
 ap.add_argument("variants", nargs="+")
 a = ap.parse_args()
+W = workloads.by_name(a.config)
 lib = capi.load()
 dev = torch.device("cuda:0")
 B = a.blocks
-cz = Channelizer(W.L, W.M, capi.KGPU_REAL, dev, capacity=a.nchan)
-for k in range(a.nchan):
-    cz.add_channel(480, W.channels[k % 1024].shift, -1 / 3, 1 / 3, 11.0)
+nchan = a.nchan or len(W.channels)
+cz = Channelizer(W.L, W.M, W.in_type, dev, capacity=nchan)
+for k in range(nchan):
+    c = W.channels[k % len(W.channels)]
+    cz.add_channel(c.olen, c.shift, c.low, c.high, c.beta)
 nstream = max(32, 4 * B)
 rng = np.random.default_rng(0)
-host = rng.integers(-3000, 3000, nstream * W.L + W.M - 1, dtype=np.int16)
+wps = 2 if W.in_type == capi.KGPU_COMPLEX else 1
+host = rng.integers(-3000, 3000, (nstream * W.L + W.M - 1) * wps, dtype=np.int16)
 d_stream = torch.from_numpy(host).to(dev)
 spec, out = cz.alloc_spectra(B), cz.alloc_outputs(B)
 ng = nstream // B
