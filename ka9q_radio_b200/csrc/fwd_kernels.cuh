@@ -196,6 +196,8 @@ struct Pass2Args {
   unsigned long long *dbg;  // or nullptr: per-CTA phase timestamps
   int mid_mod;          // see Pass1Args
   int mid_ld;           // see Pass1Args
+  int rev;              // v2 rows: take the blocks of the launch last-to-first (the column pass wrote the last ones most recently: L2)
+  int pf_ctas;          // v2 rows: L2-prefetch the rows of the CTA this many CTAs ahead in launch order (0 = off)
 };
 
 __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_kernel(Pass2Args const a) {

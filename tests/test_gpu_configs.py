@@ -58,7 +58,7 @@ def _run_and_check(oracle, cuda_dev, w, nstream, B, first_block, check_blocks):
         # included (measured here: up to 1.5e-7 of the loudest channel, peak over 1.5 M samples).  So channels more than 30 dB
         # below the loudest are measured against that -30 dB level; channels within 20 dB of the loudest must agree to 1e-5 of
         # their own peak (they agree to ~3e-7).  test_cfg2_quiet_channels_no_worse_than_the_float32_oracle shows against a
-        # float64 transform that the GPU's share of that difference is not the larger one.
+        # float64 transform that both sit on the same rounding floor (rms within 2x; the GPU's spectrum error is the smaller).
         own = float(np.abs(r).max())
         e = float(np.abs(g - r).max()) / max(own, 3e-2 * loud)
         if own >= 0.1 * loud:
@@ -80,12 +80,15 @@ def test_cfg2_all_channels_32_block_launch(oracle, cuda_dev):
 
 def test_cfg2_quiet_channels_no_worse_than_the_float32_oracle(oracle, cuda_dev):
     """The justification of the -40 dB floor above: against a float64 transform of the same block, the GPU's error on
-    noise-only channels is no larger than the float32 oracle's (both are the same rounding-noise floor)."""
+    noise-only channels is the same rounding-noise floor as the float32 oracle's.  Measured on a B200 (tools/diag_floor.py,
+    nine quiet channels): oracle max 1.09e-9 / rms 2.9e-10; GPU 1.41e-9 / 3.8e-10 (50 x 25 rows), 1.03e-9 / 3.8e-10
+    (10 x 25 x 5 rows), 0.98e-9 / 3.5e-10 (runtime-plan kernels); spectrum rms error 3.97e-5 (GPU) vs 4.39e-5 (oracle) on
+    max|X| = 7.2e4.  The rms is the statistic (the max of ~4000 noise-like samples moves by +-30 % between kernel variants)."""
     from ka9q_radio_b200 import workloads
     from ka9q_radio_b200.channelizer import Channelizer
 
     w = workloads.cfg2()
-    quiet = [9, 100, 500, 777, 1000]          # no tone within 150 kHz
+    quiet = [9, 100, 500, 777, 1000, 33, 250, 640, 900]          # no tone within 150 kHz
     w.channels = [w.channels[i] for i in quiet] + [w.channels[3]]   # + one tone channel as the loudness reference
     xi = w.stream(2)
     xf = oracle.convert_i16(xi, np.float32(w.scale))[0]
@@ -97,6 +100,7 @@ def test_cfg2_quiet_channels_no_worse_than_the_float32_oracle(oracle, cuda_dev):
     cz.channels(spec, 2, out)
     torch.cuda.synchronize()
     got = out.cpu().numpy()
+    gspec = spec.cpu().numpy()[1, : w.N // 2 + 1]
     offs = [cz.bank.out_offset(i) for i in range(len(w.channels))]
     cz.close()
     b = 1
@@ -105,7 +109,7 @@ def test_cfg2_quiet_channels_no_worse_than_the_float32_oracle(oracle, cuda_dev):
     X64 = oracle.forward_real_f64(win.astype(np.float64))
     R = oracle.design_response(600, 480, w.N, True, w.channels[0].low, w.channels[0].high, 11.0)
     k = np.arange(-300, 300)
-    e_gpu, e_ora = 0.0, 0.0
+    eg, eo = [], []
     for i, c in enumerate(w.channels[:-1]):
         S = np.zeros(600, np.complex128)
         S[k % 600] = X64[c.shift + k] * R[k % 600].astype(np.complex128)
@@ -113,9 +117,15 @@ def test_cfg2_quiet_channels_no_worse_than_the_float32_oracle(oracle, cuda_dev):
         truth = (np.fft.ifft(S) * 600)[-480:]
         r32 = oracle.channel_block(oracle.KO_REAL, X32, R, c.shift)[-480:]
         g = got[b, offs[i]: offs[i] + 480]
-        e_gpu = max(e_gpu, float(np.abs(g - truth).max()))
-        e_ora = max(e_ora, float(np.abs(r32 - truth).max()))
-    assert e_gpu < 2.0 * e_ora, (e_gpu, e_ora)
+        eg.append(np.abs(g - truth))
+        eo.append(np.abs(r32 - truth))
+    eg, eo = np.concatenate(eg), np.concatenate(eo)
+    rms = lambda e: float(np.sqrt((e ** 2).mean()))
+    assert rms(eg) < 2.0 * rms(eo), (rms(eg), rms(eo))
+    assert float(eg.max()) < 3.0 * float(eo.max()), (float(eg.max()), float(eo.max()))
+    nb = w.N // 2 + 1
+    sg, so = np.abs(gspec - X64[:nb]), np.abs(X32[:nb] - X64[:nb])
+    assert rms(sg) < 1.5 * rms(so), (rms(sg), rms(so))
 
 
 def test_cfg3_all_300_channels(oracle, cuda_dev):
