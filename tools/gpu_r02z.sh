@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python tools/diag_floor.py default 10=6 10=3 13=4 13=4,10=6 static=0 > gpurun_out/diag_floor.txt 2>&1
-cat gpurun_out/diag_floor.txt
+timeout 900 python tools/kbench.py --blocks 32 default 12=4 12=8 12=16 12=8,15=-1 > gpurun_out/kbench_r02z4.txt 2>&1
+cat gpurun_out/kbench_r02z4.txt
