@@ -189,7 +189,7 @@ template <int RC, int RD> struct Rows2sShape {
 };
 
 template <int RC, int RD>
-__global__ void __launch_bounds__((Rows2sShape<RC, RD>::T), 2) fwd_rows_2s(Pass2Args const a, float2 const *tw0) {
+__global__ void __launch_bounds__((Rows2sShape<RC, RD>::T), 3) fwd_rows_2s(Pass2Args const a, float2 const *tw0) {
   using S = Rows2sShape<RC, RD>;
   constexpr int PITCH = S::PITCH;
   extern __shared__ __align__(16) unsigned char smem_raw[];

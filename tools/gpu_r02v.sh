@@ -7,7 +7,7 @@ for c in cfg3 cfg4; do
   timeout 900 python bench.py --config $c --no-filter-h > gpurun_out/bench_r02_$c.json 2> gpurun_out/bench_r02_$c.err
 done
 timeout 900 python bench.py --impl reference --steps 2 --warmup 3 > gpurun_out/bench_r02_reference_arm.json 2> gpurun_out/bench_r02_reference_arm.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 6 -c 60 --csv --log-file gpurun_out/launches_r02.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'fwd_|chan_|notch' -s 6 -c 60 --csv --log-file gpurun_out/launches_r02.csv \
     python bench.py --steps 4 --warmup 3 --quick --no-cpu-baseline > gpurun_out/launches_r02.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'fwd_cols_r36|fwd_rows_r50|chan_v2' -s 6 -c 3 -o gpurun_out/prof_r02_final -f \
     python tools/kbench.py --blocks 32 --iters 2 --rounds 1 default > gpurun_out/ncu_r02_final.log 2>&1
