@@ -569,8 +569,7 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
         for (int j = 0; j < RS::RD; j++) r0[(size_t)e * RS::RD + j] = root((long)j * Pow<RS::RC>::exponent(e), 1250);
       CUDA_OKP(cudaMalloc(&m->d_r50_tw0, sizeof(float2) * r0.size()));
       CUDA_OKP(cudaMemcpy(m->d_r50_tw0, r0.data(), sizeof(float2) * r0.size(), cudaMemcpyHostToDevice));
-      if (set_smem((const void *)fwd_rows_r50<1296, true>, RS::smem) || set_smem((const void *)fwd_rows_r50<0, true>, RS::smem) ||
-          set_smem((const void *)fwd_rows_r50<0, false>, RS::smem)) {
+      if (set_smem((const void *)fwd_rows_r50<1296, true>, RS::smem) || set_smem((const void *)fwd_rows_r50<0, false>, RS::smem)) {
         kgpu_master_destroy(m);
         return nullptr;
       }
@@ -819,8 +818,7 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
       size_t const sv2 = sizeof(float2) * (8 * 1250 + 1246);
       if (a2.real_split && g_tuning[10].load() == 0) {  // default: two fat stages (50 x 25); 10=6: the 10 x 25 x 5 kernel (A/B)
         using RS = RowsR50Shape;
-        if (halved && m->sp.n1 == 1296) fwd_rows_r50<1296, true><<<g2, RS::T, RS::smem, st>>>(a2, tb, m->d_r50_tw0);
-        else if (halved) fwd_rows_r50<0, true><<<g2, RS::T, RS::smem, st>>>(a2, tb, m->d_r50_tw0);
+        if (halved) fwd_rows_r50<1296, true><<<g2, RS::T, RS::smem, st>>>(a2, tb, m->d_r50_tw0);  // halved <=> 36 x 36 columns in front
         else fwd_rows_r50<0, false><<<g2, RS::T, RS::smem, st>>>(a2, tb, m->d_r50_tw0);
       } else if (a2.real_split && halved && g_tuning[10].load() == 3) fwd_rows_v2<true, 1296, true, false, 0, false><<<g2, 256, sv2, st>>>(a2, tb);  // A/B: stage-0 twiddles by loads
       else if (a2.real_split && halved && g_tuning[10].load() == 5) fwd_rows_v2<true, 1296, true, false, 0, true, true><<<g2, 256, sv2, st>>>(a2, tb);  // A/B: stage-1 twiddles by products

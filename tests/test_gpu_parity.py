@@ -150,6 +150,37 @@ def test_forward_full_size_vs_oracle(oracle, cuda_dev, static):
     capi.load().kgpu_use_static_kernels(1)
 
 
+@pytest.mark.parametrize("L,M,shape", [(2560000, 640001, "1280 x 1250"), (2592000, 648001, "1296 x 1250")])
+def test_forward_real_1250_columns_row_kernel_variants(oracle, cuda_dev, L, M, shape):
+    """The 50 x 25 row kernel serves every REAL master with 1250 columns: with the 36 x 36 column kernel in front of it
+    (1296 rows, the 1/2 of the split pre-folded) and with the runtime-plan column kernel (any other row count, here 1280);
+    both also against the 10 x 25 x 5 kernel it replaced (tuning 10 = 6).  Two blocks, float input."""
+    from ka9q_radio_b200 import capi
+
+    lib = capi.load()
+    rng = np.random.default_rng(12)
+    x = (0.1 * rng.standard_normal(2 * L)).astype(np.float32)
+    t = np.arange(2 * L)
+    x += (0.5 * np.cos(2 * np.pi * ((0.2345 * t) % 1.0))).astype(np.float32)
+    cz = _mk(L, M, capi.KGPU_REAL, cuda_dev)
+    assert shape in cz.master.describe()
+    d = cz.stage_stream(x)
+    spec, spec_old = cz.alloc_spectra(2), cz.alloc_spectra(2)
+    cz.forward(d, 2, spec)
+    lib.kgpu_set_tuning(10, 6)
+    cz.forward(d, 2, spec_old)
+    lib.kgpu_set_tuning(10, 0)
+    torch.cuda.synchronize()
+    nb = cz.master.bins
+    got, old = spec.cpu().numpy()[:, :nb], spec_old.cpu().numpy()[:, :nb]
+    for b in range(2):
+        ref = oracle.forward(oracle.block_window(x, L, M, b))
+        assert rel_err(got[b], ref) < TOL, (b, rel_err(got[b], ref))
+        assert rel_err(old[b], ref) < TOL
+    assert np.abs(got - old).max() / np.abs(old).max() < 2e-6
+    cz.close()
+
+
 def test_notches(oracle, cuda_dev):
     from ka9q_radio_b200 import capi
 
