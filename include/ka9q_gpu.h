@@ -157,15 +157,12 @@ int kgpu_bank_commit(kgpu_bank *b, void *stream);
  * kernel exists (both are parity-tested). Default 1. */
 int kgpu_use_static_kernels(int on);
 
-/* Experiment knobs for A/B measurements (0 = shipped default everywhere).  key 13: column pass of the 1296 x n2
- * transform: 0 = 36 x 36 two-stage kernel (default), 4 = round-1 12 x 12 x 9 kernel, 1 / 2 = that kernel with 16 / 6-column tiles;
- * key 2: 1 / 2 = table twiddles / I2F unpack in the 12 x 12 x 9 kernel; key 3: L2 prefetch of the input (1 = separate kernel,
- * d+1 = in-kernel, d blocks ahead); key 6: 1 = channel kernel's stage-0 twiddles by products; key 10: row pass of a REAL
- * n1 x 1250 transform: 0 = 50 x 25 two-stage kernel (default), 6 = 10 x 25 x 5 kernel, and on that kernel 1 = warp-per-column
- * stages, 2 / 4 = stage-0 butterflies in groups, 3 = stage-0 twiddles by loads, 5 = stage-1 twiddles by products; key 11: 1 = TMA tile store in the
- * 12 x 12 x 9 kernel; key 12: S = forward transform in sub-batches of S blocks on two internal streams; key 14: 1 = row pass
- * takes the blocks first-to-last (default last-to-first: L2 reuse of the column pass's output); key 15: row pass's L2 prefetch
- * distance in CTAs (0 = one SM count, -1 = off). */
+/* A/B knobs (0 = shipped default everywhere).  key 13: 4 = column pass of the 1296 x n2 transform on the round-1 12 x 12 x 9
+ * kernel instead of the 36 x 36 one; key 10: 6 = row pass of a REAL n1 x 1250 transform on the 10 x 25 x 5 kernel instead of the
+ * 50 x 25 one; key 14: 1 = row pass takes the blocks first-to-last (default last-to-first: L2 reuse of the column pass's
+ * output); key 15: row pass's L2 prefetch distance in CTAs (0 = one SM count, -1 = off).  The experiments that lost
+ * (tile widths, TMA tile store, sub-batched forward, prefetches elsewhere ...) are listed with their numbers in
+ * profiles/README.md and are no longer in the library. */
 int kgpu_set_tuning(int key, int value);
 
 /* Diagnostics: device buffer (6 uint64 per CTA of the cols kernel) receiving globaltimer stamps

@@ -86,7 +86,6 @@ struct ChanArgs {
   long block0;         // bank block counter of this launch's block 0 (oscillator epoch arithmetic)
   float *power;        // nullptr or [block][power_stride]: mean |y|^2 of each kChanOsc channel's block (radio.c:1515-1520)
   long power_stride;
-  int pf_ctas;         // chan_v2: L2-prefetch the bin slices of the CTA this many CTAs ahead in launch order (0 = off)
 };
 
 __global__ void __launch_bounds__(kChanWarps * 32) chan_kernel(ChanArgs const a) {

@@ -40,8 +40,6 @@ struct Pass1Args {
   IngestStats *stats;   // or nullptr
   unsigned long long *dbg;  // or nullptr: per-CTA phase timestamps (globaltimer ns) for tools/phase_trace.py
   float out_scale;      // v2 kernels: factor folded into the inter-pass twiddle (int16 scale, x0.5 when the split is pre-halved)
-  int pf_dist;          // blocks of look-ahead for the in-kernel L2 prefetch of the input stream (0 = off)
-  int mid_mod;          // experiment (tuning 7): alias the inter-pass buffer of block b onto b % mid_mod (0 = off)
   int mid_ld;           // elements between consecutive k1 rows of `mid` (>= n2; the 36 x 36 kernel pads rows to 128 bytes)
 };
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -194,7 +192,6 @@ struct Pass2Args {
   float2 *spec;         // [block][spec_stride]
   long spec_stride;
   unsigned long long *dbg;  // or nullptr: per-CTA phase timestamps
-  int mid_mod;          // see Pass1Args
   int mid_ld;           // see Pass1Args
   int rev;              // v2 rows: take the blocks of the launch last-to-first (the column pass wrote the last ones most recently: L2)
   int pf_ctas;          // v2 rows: L2-prefetch the rows of the CTA this many CTAs ahead in launch order (0 = off)
@@ -303,14 +300,6 @@ __global__ void __launch_bounds__(kFwdThreads, 2) fwd_rows_kernel(Pass2Args cons
   }
   for (; k2 < kend; k2 += qstep)
     emit(k2, ca[__ldg(pl.perm + k2)], cb[__ldg(pl.perm + partner(k2))], __ldg(a.rootD + k2));
-}
-
-// Pull a byte range into L2 with fully coalesced requests (the column pass then reads it in 32-byte
-// pieces at a 5 kB stride, which DRAM serves poorly but L2 serves well).
-__global__ void l2_prefetch_kernel(char const *base, long bytes) {
-  long const lines = (bytes + 127) / 128;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < lines; i += (long)gridDim.x * blockDim.x)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + i * 128));
 }
 
 // ---------------------------------------------------------------------------------------------

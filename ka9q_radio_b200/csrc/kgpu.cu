@@ -417,10 +417,6 @@ struct kgpu_master {
   float2 *d_r50_tw0 = nullptr;           // 50 x 25 row kernel (REAL masters with 1250 columns)
   float2 *d_mid = nullptr;
   int mid_blocks = 0;
-  cudaStream_t aux[2] = {nullptr, nullptr};   // internal streams of the sub-batched forward (tuning 12)
-  cudaEvent_t aux_done[2] = {nullptr, nullptr}, aux_start = nullptr;
-  alignas(64) CUtensorMap mid_map{};  // 5-D view (n2, t2, t1, t0, block) of d_mid for the TMA tile store of fwd_cols_v2<.., TMAST>
-  bool mid_map_ok = false;
   size_t smem1 = 0, smem2 = 0;
   // notches
   NotchDev *d_notch = nullptr;
@@ -581,20 +577,13 @@ extern "C" kgpu_master *kgpu_master_create(int L, int M, int in_type) {
         set_smem((const void *)fwd_cols_v2<2>, sv1) || set_smem((const void *)fwd_rows_v2<true>, sv2) ||
         set_smem((const void *)fwd_rows_v2<false>, sv2) ||
         set_smem((const void *)fwd_cols_v2<0, 1250>, sv1) || set_smem((const void *)fwd_cols_v2<1, 1250>, sv1) ||
-        set_smem((const void *)fwd_cols_v2<2, 1250>, sv1) || set_smem((const void *)fwd_cols_v2<1, 1250, 1>, sv1) || set_smem((const void *)fwd_cols_v2<1, 1250, 2>, sv1) ||
-        set_smem((const void *)fwd_rows_v2<true, 1296, true>, sv2) || set_smem((const void *)fwd_rows_v2<true, 1296, true, true>, sv2) ||
-        set_smem((const void *)fwd_cols_v2<0, 1250, 0, true>, sv1 + 128) || set_smem((const void *)fwd_cols_v2<1, 1250, 0, true>, sv1 + 128) ||
-        set_smem((const void *)fwd_cols_v2<2, 1250, 0, true>, sv1 + 128) ||
-        set_smem((const void *)fwd_cols_v2<1, 1250, 0, false, 16>, sizeof(float2) * (16 * 1297 + 1288 + 160)) ||
-        set_smem((const void *)fwd_cols_v2<1, 1250, 0, false, 6>, sizeof(float2) * (6 * 1298 + 1288 + 60)) ||
+        set_smem((const void *)fwd_cols_v2<2, 1250>, sv1) || set_smem((const void *)fwd_rows_v2<true, 1296, true>, sv2) ||
         set_smem((const void *)fwd_cols_r36<0, 1250>, sizeof(float2) * (8 * 1378 + 440)) ||
         set_smem((const void *)fwd_cols_r36<1, 1250>, sizeof(float2) * (8 * 1378 + 440)) ||
         set_smem((const void *)fwd_cols_r36<2, 1250>, sizeof(float2) * (8 * 1378 + 440)) ||
         set_smem((const void *)fwd_cols_r36<0, 0>, sizeof(float2) * (8 * 1378 + 440)) ||
         set_smem((const void *)fwd_cols_r36<1, 0>, sizeof(float2) * (8 * 1378 + 440)) ||
         set_smem((const void *)fwd_cols_r36<2, 0>, sizeof(float2) * (8 * 1378 + 440)) ||
-        set_smem((const void *)fwd_rows_v2<true, 1296, true, false, 0, false>, sv2) || set_smem((const void *)fwd_rows_v2<true, 1296, true, false, 0, true, true>, sv2) ||
-        set_smem((const void *)fwd_rows_v2<true, 1296, true, false, 2>, sv2) || set_smem((const void *)fwd_rows_v2<true, 1296, true, false, 4>, sv2) ||
         set_smem((const void *)fwd_rows_v2<false, 1296, false>, sv2)) {
       kgpu_master_destroy(m);
       return nullptr;
@@ -625,11 +614,6 @@ extern "C" void kgpu_master_destroy(kgpu_master *m) {
   cudaFree(m->d_twT);
   cudaFree(m->d_mid);
   cudaFree(m->d_notch);
-  for (int i = 0; i < 2; i++) {
-    if (m->aux[i]) cudaStreamDestroy(m->aux[i]);
-    if (m->aux_done[i]) cudaEventDestroy(m->aux_done[i]);
-  }
-  if (m->aux_start) cudaEventDestroy(m->aux_start);
   delete m;
 }
 extern "C" int kgpu_master_points(kgpu_master const *m) { return m ? m->N : -1; }
@@ -660,32 +644,6 @@ extern "C" int kgpu_master_describe(kgpu_master const *m, char *buf, int buflen)
   return 0;
 }
 
-// 5-D tensor map of the inter-pass buffer for the column pass's tile store: coordinates
-// (n2, t2, t1, t0, block) with k1 = t0 + 12 t1 + 144 t2, box = one 8-column tile.  The encoder lives in
-// the driver (libcuda); it is looked up at run time so that the library links against cudart only.
-static bool encode_mid_map(kgpu_master *m) {
-  typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static encode_fn fn = nullptr;
-  if (!fn) {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) {
-      cudaGetLastError();
-      return false;
-    }
-    fn = (encode_fn)p;
-  }
-  cuuint64_t const n2 = (cuuint64_t)m->sp.n2;
-  cuuint64_t dims[5] = {n2, 9, 12, 12, (cuuint64_t)m->mid_blocks};
-  cuuint64_t strides[4] = {144 * n2 * 8, 12 * n2 * 8, n2 * 8, (cuuint64_t)m->nc * 8};
-  cuuint32_t box[5] = {8, 9, 12, 3, 1}, estr[5] = {1, 1, 1, 1, 1};
-  CUresult const r = fn(&m->mid_map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, m->d_mid, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
 // One launch pair (column pass, row pass) over `nblocks` consecutive blocks on stream `st`, inter-pass data in `mid`.
 static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, int derandomize, int nblocks, void *d_spec,
                         void *d_stats, cudaStream_t st, float2 *mid) {
@@ -703,16 +661,8 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
   a1.mid = mid;
   a1.stats = (fmt == KGPU_FMT_I16) ? (IngestStats *)d_stats : nullptr;
   a1.dbg = (unsigned long long *)g_dbg_buf;
-  a1.mid_mod = 0;
   a1.mid_ld = m->sp.n2;
-  a1.pf_dist = g_tuning[3].load() >= 2 ? g_tuning[3].load() - 1 : 0;
   dim3 const g1((unsigned)((m->sp.n2 + kTile - 1) / kTile), (unsigned)nblocks);
-  if (g_tuning[3].load() == 1) {  // experiment: pull the input windows into L2 with coalesced requests first
-    long const esz = (m->in_type == KGPU_REAL) ? (fmt == KGPU_FMT_I16 ? 2 : 4) : (fmt == KGPU_FMT_I16 ? 4 : 8);
-    long const bytes = ((long)(nblocks - 1) * m->L + m->N) * esz;
-    l2_prefetch_kernel<<<148 * 4, 256, 0, st>>>((char const *)d_in, bytes);
-    g_launches++;
-  }
   FwdTables tb;
   tb.rootC = m->d_rootC;
   bool const use_static = g_static_on.load() != 0;
@@ -741,11 +691,7 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
       // folded into the inter-pass twiddle
       halved = (m->in_type == KGPU_REAL) && m->static_rows == 1250;
       a1.out_scale = (fmt == KGPU_FMT_I16 ? scale : 1.0f) * (halved ? 0.5f : 1.0f);
-      if (m->sp.n2 == 1250 && m->mid_map_ok && g_tuning[11].load() == 1) {  // TMA tile store
-        if (f == 0) fwd_cols_v2<0, 1250, 0, true><<<g1, 288, sv1 + 128, st>>>(a1, t2, m->mid_map);
-        else if (f == 1) fwd_cols_v2<1, 1250, 0, true><<<g1, 288, sv1 + 128, st>>>(a1, t2, m->mid_map);
-        else fwd_cols_v2<2, 1250, 0, true><<<g1, 288, sv1 + 128, st>>>(a1, t2, m->mid_map);
-      } else if (g_tuning[13].load() == 0) {  // default: two fat stages (36 x 36), one trip through shared memory
+      if (g_tuning[13].load() == 0) {  // default: two fat stages (36 x 36), one trip through shared memory
         if (m->sp.n2 == 1250 && m->static_rows == 1250) a1.mid_ld = (m->sp.n2 + 15) / 16 * 16;  // rows padded to 128 B (both kernels know)
         size_t const sr = sizeof(float2) * (8 * 1378 + 440);
         ColsR36Tables t3;
@@ -761,24 +707,14 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
           else if (f == 1) fwd_cols_r36<1, 0><<<g1, 288, sr, st>>>(a1, t3);
           else fwd_cols_r36<2, 0><<<g1, 288, sr, st>>>(a1, t3);
         }
-      } else if (m->sp.n2 == 1250 && f == 1 && g_tuning[13].load() == 2) {  // 6-column tiles, three CTAs per SM
-        size_t const sv6 = sizeof(float2) * (6 * 1298 + 1288 + 60);
-        dim3 const g6((unsigned)((m->sp.n2 + 5) / 6), (unsigned)nblocks);
-        fwd_cols_v2<1, 1250, 0, false, 6><<<g6, 216, sv6, st>>>(a1, t2, m->mid_map);
-      } else if (m->sp.n2 == 1250 && f == 1 && g_tuning[13].load() == 1) {  // 16-column tiles, one CTA per SM
-        size_t const sv16 = sizeof(float2) * (16 * 1297 + 1288 + 160);
-        dim3 const g16((unsigned)((m->sp.n2 + 15) / 16), (unsigned)nblocks);
-        fwd_cols_v2<1, 1250, 0, false, 16><<<g16, 576, sv16, st>>>(a1, t2, m->mid_map);
       } else if (m->sp.n2 == 1250) {
-        if (f == 0) fwd_cols_v2<0, 1250><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
-        else if (f == 1 && g_tuning[2].load() == 1) fwd_cols_v2<1, 1250, 1><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
-        else if (f == 1 && g_tuning[2].load() == 2) fwd_cols_v2<1, 1250, 2><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
-        else if (f == 1) fwd_cols_v2<1, 1250><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
-        else fwd_cols_v2<2, 1250><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
+        if (f == 0) fwd_cols_v2<0, 1250><<<g1, 288, sv1, st>>>(a1, t2);
+        else if (f == 1) fwd_cols_v2<1, 1250><<<g1, 288, sv1, st>>>(a1, t2);
+        else fwd_cols_v2<2, 1250><<<g1, 288, sv1, st>>>(a1, t2);
       } else {
-        if (f == 0) fwd_cols_v2<0><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
-        else if (f == 1) fwd_cols_v2<1><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
-        else fwd_cols_v2<2><<<g1, 288, sv1, st>>>(a1, t2, m->mid_map);
+        if (f == 0) fwd_cols_v2<0><<<g1, 288, sv1, st>>>(a1, t2);
+        else if (f == 1) fwd_cols_v2<1><<<g1, 288, sv1, st>>>(a1, t2);
+        else fwd_cols_v2<2><<<g1, 288, sv1, st>>>(a1, t2);
       }
     } else if (fmt == KGPU_FMT_I16)
       fwd_cols_kernel<1><<<g1, kFwdThreads, m->smem1, st>>>(a1);
@@ -799,7 +735,6 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
   a2.spec = (float2 *)d_spec;
   a2.spec_stride = m->spec_stride;
   a2.dbg = g_dbg_buf2 ? (unsigned long long *)g_dbg_buf2 : nullptr;
-  a2.mid_mod = 0;
   a2.mid_ld = a1.mid_ld;
   // The row pass reads what the column pass has just written: taking the blocks last-to-first finds the most recent ones
   // still in L2, and every CTA pulls the rows of the CTA one SM-count later in launch order into L2 while it works, so
@@ -820,12 +755,7 @@ static int forward_span(kgpu_master *m, const void *d_in, int fmt, float scale, 
         using RS = RowsR50Shape;
         if (halved) fwd_rows_r50<1296, true><<<g2, RS::T, RS::smem, st>>>(a2, tb, m->d_r50_tw0);  // halved <=> 36 x 36 columns in front
         else fwd_rows_r50<0, false><<<g2, RS::T, RS::smem, st>>>(a2, tb, m->d_r50_tw0);
-      } else if (a2.real_split && halved && g_tuning[10].load() == 3) fwd_rows_v2<true, 1296, true, false, 0, false><<<g2, 256, sv2, st>>>(a2, tb);  // A/B: stage-0 twiddles by loads
-      else if (a2.real_split && halved && g_tuning[10].load() == 5) fwd_rows_v2<true, 1296, true, false, 0, true, true><<<g2, 256, sv2, st>>>(a2, tb);  // A/B: stage-1 twiddles by products
-      else if (a2.real_split && halved && g_tuning[10].load() == 2) fwd_rows_v2<true, 1296, true, false, 2><<<g2, 256, sv2, st>>>(a2, tb);
-      else if (a2.real_split && halved && g_tuning[10].load() == 4) fwd_rows_v2<true, 1296, true, false, 4><<<g2, 256, sv2, st>>>(a2, tb);
-      else if (a2.real_split && halved && g_tuning[10].load() == 1) fwd_rows_v2<true, 1296, true, true><<<g2, 256, sv2, st>>>(a2, tb);
-      else if (a2.real_split && halved) fwd_rows_v2<true, 1296, true><<<g2, 256, sv2, st>>>(a2, tb);
+      } else if (a2.real_split && halved) fwd_rows_v2<true, 1296, true><<<g2, 256, sv2, st>>>(a2, tb);
       else if (a2.real_split) fwd_rows_v2<true><<<g2, 256, sv2, st>>>(a2, tb);
       else if (m->sp.n1 == 1296) fwd_rows_v2<false, 1296, false><<<g2, 256, sv2, st>>>(a2, tb);
       else fwd_rows_v2<false><<<g2, 256, sv2, st>>>(a2, tb);
@@ -848,39 +778,9 @@ extern "C" int kgpu_forward(kgpu_master *m, const void *d_in, int fmt, float sca
     m->mid_blocks = 0;
     CUDA_OK(cudaMalloc(&m->d_mid, sizeof(float2) * (size_t)m->sp.n1 * (size_t)((m->sp.n2 + 15) / 16 * 16) * (size_t)nblocks));
     m->mid_blocks = nblocks;
-    m->mid_map_ok = (m->static_cols == 1296) && encode_mid_map(m);
   }
   if (fmt == KGPU_FMT_I16 && d_stats) CUDA_OK(cudaMemsetAsync(d_stats, 0, sizeof(IngestStats) * (size_t)nblocks, st));
-  int const sub = g_tuning[12].load();
-  if (sub <= 0 || 2 * sub > nblocks) return forward_span(m, d_in, fmt, scale, derandomize, nblocks, d_spec, d_stats, st, m->d_mid);
-  // Experiment (tuning 12 = S): sub-batches of S blocks alternate between two internal streams, each with its own
-  // S-block half of the inter-pass buffer, so that `mid` (13 MB per block) is re-read from L2 instead of DRAM and
-  // the tail of one launch overlaps the head of the next.
-  if (!m->aux[0]) {
-    for (int i = 0; i < 2; i++) {
-      CUDA_OK(cudaStreamCreateWithFlags(&m->aux[i], cudaStreamNonBlocking));
-      CUDA_OK(cudaEventCreateWithFlags(&m->aux_done[i], cudaEventDisableTiming));
-    }
-    CUDA_OK(cudaEventCreateWithFlags(&m->aux_start, cudaEventDisableTiming));
-  }
-  CUDA_OK(cudaEventRecord(m->aux_start, st));
-  CUDA_OK(cudaStreamWaitEvent(m->aux[0], m->aux_start, 0));
-  CUDA_OK(cudaStreamWaitEvent(m->aux[1], m->aux_start, 0));
-  size_t const in_bytes_per_block =
-      (size_t)m->L * ((m->in_type == KGPU_REAL) ? (fmt == KGPU_FMT_I16 ? 2 : 4) : (fmt == KGPU_FMT_I16 ? 4 : 8));
-  for (int s = 0, b0 = 0; b0 < nblocks; s++, b0 += sub) {
-    int const nb = std::min(sub, nblocks - b0);
-    int const rc = forward_span(m, (char const *)d_in + (size_t)b0 * in_bytes_per_block, fmt, scale, derandomize, nb,
-                                (float2 *)d_spec + (size_t)b0 * (size_t)m->spec_stride,
-                                d_stats ? (void *)((IngestStats *)d_stats + b0) : nullptr, m->aux[s & 1],
-                                m->d_mid + (size_t)(s & 1) * (size_t)sub * (size_t)m->sp.n1 * (size_t)((m->sp.n2 + 15) / 16 * 16));
-    if (rc) return rc;
-  }
-  for (int i = 0; i < 2; i++) {
-    CUDA_OK(cudaEventRecord(m->aux_done[i], m->aux[i]));
-    CUDA_OK(cudaStreamWaitEvent(st, m->aux_done[i], 0));
-  }
-  return 0;
+  return forward_span(m, d_in, fmt, scale, derandomize, nblocks, d_spec, d_stats, st, m->d_mid);
 }
 
 extern "C" int kgpu_master_set_notches(kgpu_master *m, int const *bins, double const *alpha, int n) {
@@ -1369,14 +1269,11 @@ template <class P> static int launch_chan_v2(ChanArgs const &a, int n, int nbloc
   size_t const sm = sizeof(float2) * ((size_t)(2 * P::len + 4) * kChanWarps + static_tw_count<P>() + 2);
   static bool attr_done = false;
   if (!attr_done) {
-    if (set_smem((const void *)chan_v2<P, false>, sm) || set_smem((const void *)chan_v2<P, true>, sm) ||
-        set_smem((const void *)chan_v2<P, false, true>, sm))
-      return -1;
+    if (set_smem((const void *)chan_v2<P, false>, sm) || set_smem((const void *)chan_v2<P, true>, sm)) return -1;
     attr_done = true;
   }
   dim3 const g((unsigned)((n + kChanWarps - 1) / kChanWarps), (unsigned)nblocks);
   if (osc) chan_v2<P, true><<<g, kChanWarps * 32, sm, st>>>(a);
-  else if (g_tuning[6].load() == 1) chan_v2<P, false, true><<<g, kChanWarps * 32, sm, st>>>(a);  // A/B: stage-0 twiddles by products
   else chan_v2<P, false><<<g, kChanWarps * 32, sm, st>>>(a);
   return 0;
 }
@@ -1414,7 +1311,6 @@ static int launch_chan(kgpu_bank *b, const void *d_spec, int nblocks, void *d_ou
   a.block0 = b->block_counter;
   a.power = d_power;
   a.power_stride = b->capacity;
-  a.pf_ctas = g_tuning[9].load() > 0 ? g_tuning[9].load() : 0;
   ProfScope ps(K_CHAN, st);
   g_launches++;
   TilePlan const *tp = host_tile_plan(plan);

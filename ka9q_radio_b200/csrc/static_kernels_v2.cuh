@@ -14,7 +14,6 @@
 // stage): no idle lanes.  Column pitch = 2 mod 16 keeps every access pattern here free of bank
 // conflicts (8 even column offsets x 2 consecutive butterflies per half-warp).
 #pragma once
-#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched from the driver at run time)
 #include "static_kernels.cuh"
 
 namespace kfft {
@@ -52,17 +51,6 @@ __device__ __forceinline__ RowItem row_item(int p, int n1, bool real_split) {
   return it;
 }
 
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_5d(CUtensorMap const *map, void const *smem, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(map), "r"(c0), "r"(c1),
-               "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(smem))
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit_and_wait_read() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
 struct ColsV2Tables {
   float2 const *twU;  // [n2][144]  W_nc^{n2 * kbase(u)}, kbase(u) = u/12 + 12*(u%12)   (u = t0*12 + t1)
   float2 const *twT;  // [n2][9]    W_nc^{n2 * 144 * t2}
@@ -71,8 +59,7 @@ struct ColsV2Tables {
 // ------------------------------------------------------------------ pass 1: columns -----------
 // FMT 0: float pairs; 1: int16 pairs; 2: int16 pairs + de-randomise + energy/clip statistics.
 // N2C: number of columns as a compile-time constant (0 = read it from the arguments): with it every
-// global address of a thread is one base register plus an immediate.  TWL: stage-0 twiddles by 11
-// table loads instead of 4 loads + 7 products.
+// global address of a thread is one base register plus an immediate.
 // int16 pair -> two floats.  `(float)(short)` compiles to I2F.S16, which issues through the MIO
 // queue to the quarter-rate conversion unit -- the queue the 36 loads and 72 shared-memory accesses
 // of a thread also need (ncu: mio_throttle was the top stall of this kernel).  Sign-extend with
@@ -87,24 +74,19 @@ __device__ __forceinline__ float i32_to_f32(int v) {
   return f;
 }
 
-// TMAST: the tile is kept column-interleaved, T[slot][8 columns]; the last stage runs in place and
-// four 5-D TMA tensor stores (box 8 x 9 x 12 x 3 x 1 over (n2, t2, t1, t0, block), k1 = t0 + 12 t1 + 144 t2),
-// one per last-stage iteration, write the tile: 36 scattered STG.64 per thread become 36 conflict-free STS.64 and the
-// 64-byte row pieces are generated by the TMA unit instead of the LSU / L1TEX pipe that bounds
-// this kernel.
-template <int FMT, int N2C = 0, int TWL = 0, bool TMAST = false, int TC = 8>
-__global__ void __launch_bounds__(36 * TC, TC == 8 ? 2 : TC == 6 ? 3 : 1) fwd_cols_v2(Pass1Args const a, ColsV2Tables const tb,
-                                                      const __grid_constant__ CUtensorMap tmap) {
+// Round-1 column pass (12 x 12 x 9, two and a half trips through shared memory); fwd_cols_r36.cuh replaced it as the default,
+// it stays selectable (kgpu_set_tuning(13, 4)) as the A/B partner.  Variants measured on it and removed again: 16- and 6-column
+// tiles (7.82 / 10.93 us per block against 6.32), a TMA tensor store of the tile (6.87), table twiddles, an L2 prefetch of
+// the next block's input (no change) -- profiles/README.md.
+template <int FMT, int N2C = 0>
+__global__ void __launch_bounds__(288, 2) fwd_cols_v2(Pass1Args const a, ColsV2Tables const tb) {
   using P = SPlan<1296, 12, 12, 9>;
-  static_assert(TC == 8 || ((TC == 16 || TC == 6) && !TMAST), "tile width");
-  // TC = 16: one 576-thread CTA per SM; a warp-wide global access then covers 2 rows x 64/128 B instead of 4 rows x 32/64 B
-  // (half the L1TEX wavefronts per byte).  Column pitch 1 mod 16: 16 columns x one butterfly per half-warp hit 32 distinct banks.
-  constexpr int N1 = 1296, PITCH = TC == 16 ? 1297 : 1298, T = 36 * TC, UPI = 36 /*butterflies per column per iteration*/;
+  constexpr int TC = 8;
+  constexpr int N1 = 1296, PITCH = 1298, UPI = 36 /*butterflies per column per iteration*/;
   constexpr int R0 = 12, S0 = 108, R1 = 12, NSUB1 = 108, S1 = 9, R2 = 9;
-  constexpr int XS = TMAST ? 8 : 1, CS = TMAST ? 1 : PITCH;  // element (column c, index X) at tile[X*XS + c*CS]
+  constexpr int XS = 1, CS = PITCH;  // element (column c, index X) at tile[X*XS + c*CS]
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  // the TMA tensor store wants a 128-byte aligned source (the launch reserves the slack)
-  float2 *tile = reinterpret_cast<float2 *>(smem_raw + (TMAST ? ((128u - (smem_u32(smem_raw) & 127u)) & 127u) : 0u));  // [8][PITCH]
+  float2 *tile = reinterpret_cast<float2 *>(smem_raw);  // [8][PITCH]
   float2 *s_tw = tile + TC * PITCH + (TC * PITCH) % 2;  // stage twiddles (1287 entries, padded to 1288), 16-byte aligned
   float2 *s_twT = s_tw + 1288;                          // [TC][9] (padded to 10 TC)
   __shared__ __align__(8) uint64_t tbar;
@@ -114,7 +96,6 @@ __global__ void __launch_bounds__(36 * TC, TC == 8 ? 2 : TC == 6 ? 3 : 1) fwd_co
   int const c0 = blockIdx.x * TC, blk = blockIdx.y;
   int const n2 = N2C ? N2C : a.n2;
   long const nc = N2C ? (long)N1 * N2C : a.nc;
-  int const mblk = a.mid_mod ? blk % a.mid_mod : blk;
   unsigned long long *dbg = a.dbg ? a.dbg + 6 * ((long)blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
   if (dbg && tid == 0) {
     dbg[0] = gtimer();
@@ -130,20 +111,6 @@ __global__ void __launch_bounds__(36 * TC, TC == 8 ? 2 : TC == 6 ? 3 : 1) fwd_co
     mbar_expect_tx(&tbar, 1288 * 8 + 10 * TC * 8);
     bulk_g2s(s_tw, pl.tw, 1288 * 8, &tbar);
     bulk_g2s(s_twT, tb.twT + (long)c0 * 9, 10 * TC * 8, &tbar);  // table padded by 16 columns + 16 entries
-  }
-  // The column gather reads 32-byte pieces at a 5 kB stride, which DRAM serves slowly.  Each CTA
-  // therefore pulls a CONTIGUOUS 1/gridDim.x share of the new samples of block blk + pf_dist into
-  // L2 (bulk prefetch, no registers, no shared memory): by the time that block's CTAs run, their
-  // gather hits L2.
-  if (a.pf_dist > 0 && blk + a.pf_dist < (int)gridDim.y && tid >= 32 && tid < 64) {
-    long const esz = FMT == 0 ? 8 : 4;
-    long const newb = a.hop * esz;                                  // new bytes per block
-    long const share = ((newb / (long)gridDim.x + 15) & ~15L);
-    long const lo = (long)blockIdx.x * share, hi = min(newb, lo + share);
-    char const *base = reinterpret_cast<char const *>(a.in) + ((long)(blk + a.pf_dist) * a.hop + (a.nc - a.hop)) * esz;
-    base = reinterpret_cast<char const *>(reinterpret_cast<unsigned long long>(base) & ~15ULL);
-    for (long o = lo + (long)(tid - 32) * 2048; o < hi; o += 32 * 2048)
-      bulk_prefetch_l2(base + o, (uint32_t)min(2048L, (hi - o) & ~15L));
   }
   __syncthreads();  // barrier initialised before anybody waits on it
   // inter-pass factors B'(n2, u) for this thread's four stage-2 butterflies: issued now, used last
@@ -171,11 +138,7 @@ __global__ void __launch_bounds__(36 * TC, TC == 8 ? 2 : TC == 6 ? 3 : 1) fwd_co
         int const j = ul + UPI * it;
         Dft<R0, false>::run(x[it]);
         float2 w[R0];
-        if (TWL == 1) {
-#pragma unroll
-          for (int t = 1; t < R0; t++) w[t] = s_tw[(t - 1) * S0 + j];
-        } else
-          load_stage_twiddles<R0, S0>(s_tw, j, w);
+        load_stage_twiddles<R0, S0>(s_tw, j, w);
         float2 *d = mycol + j * XS;
         d[0] = x[it][0];
 #pragma unroll
@@ -197,11 +160,7 @@ __global__ void __launch_bounds__(36 * TC, TC == 8 ? 2 : TC == 6 ? 3 : 1) fwd_co
 #pragma unroll
         for (int m = 0; m < R0; m++) {
           int lo, hi;
-          if (TWL == 2) {  // A/B: the I2F.S16 form
-            lo = (short)(raw[it][m] & 0xffff);
-            hi = (short)((unsigned)raw[it][m] >> 16);
-          } else
-            unpack_i16(raw[it][m], lo, hi);
+          unpack_i16(raw[it][m], lo, hi);
           if (FMT == 2) {
             if (a.derandomize) {  // lsb set -> flip bits 1..15 (rx888.c:707-712); on the sign-extended word: bits 1..31
               lo ^= (lo & 1) ? 0xfffffffe : 0;
@@ -212,16 +171,11 @@ __global__ void __launch_bounds__(36 * TC, TC == 8 ? 2 : TC == 6 ? 3 : 1) fwd_co
               clips += (lo > 32766 || lo < -32766) + (hi > 32766 || hi < -32766);
             }
           }
-          x[m] = (TWL == 2) ? make_float2((float)(short)lo, (float)(short)hi)
-                            : make_float2(i32_to_f32(lo), i32_to_f32(hi));  // the int16 scale rides on the inter-pass twiddle
+          x[m] = make_float2(i32_to_f32(lo), i32_to_f32(hi));  // the int16 scale rides on the inter-pass twiddle
         }
         Dft<R0, false>::run(x);
         float2 w[R0];
-        if (TWL == 1) {
-#pragma unroll
-          for (int t = 1; t < R0; t++) w[t] = s_tw[(t - 1) * S0 + j];
-        } else
-          load_stage_twiddles<R0, S0>(s_tw, j, w);
+        load_stage_twiddles<R0, S0>(s_tw, j, w);
         float2 *d = mycol + j * XS;
         d[0] = x[0];
 #pragma unroll
@@ -274,7 +228,7 @@ __global__ void __launch_bounds__(36 * TC, TC == 8 ? 2 : TC == 6 ? 3 : 1) fwd_co
     for (int t = 0; t < R2; t++) wT[t] = s_twT[c * 9 + t];
     // u = ul + 36 it = t0*12 + t1 -> k1 = kbase + 144 t2 with kbase = t0 + 12 t1 = kbase(ul) + 3 it
     int const kb0 = ul / 12 + 12 * (ul % 12);
-    float2 *dst = a.mid + (long)mblk * nc + n2g + (long)kb0 * n2;
+    float2 *dst = a.mid + (long)blk * nc + n2g + (long)kb0 * n2;
     float const os = a.out_scale;
 #pragma unroll
     for (int it = 0; it < 4; it++) {
@@ -288,22 +242,11 @@ __global__ void __launch_bounds__(36 * TC, TC == 8 ? 2 : TC == 6 ? 3 : 1) fwd_co
         float2 const wb = make_float2(twU[it].x * os, twU[it].y * os);
 #pragma unroll
         for (int t = 0; t < R2; t++) {
-          float2 const y = cmul(x[t], cmul(wb, wT[t]));
-          if (TMAST) p[t * XS] = y;  // in place: slot 9u + t2 = 108 t0 + 9 t1 + t2 holds k1 = t0 + 12 t1 + 144 t2
-          else dst[(long)(3 * it + 144 * t) * n2] = y;
-        }
-      }
-      if (TMAST) {  // iteration `it` completed t0 = 3 it .. 3 it + 2: a contiguous quarter of the tile goes out now
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-          tma_store_5d(&tmap, tile + 2592 * it, c0, 0, 0, 3 * it, mblk);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          dst[(long)(3 * it + 144 * t) * n2] = cmul(x[t], cmul(wb, wT[t]));
         }
       }
     }
   }
-  if (TMAST && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // tile stays allocated until read
   if (dbg && tid == 0) dbg[3] = gtimer();
 }
 
@@ -314,23 +257,19 @@ __global__ void __launch_bounds__(36 * TC, TC == 8 ? 2 : TC == 6 ? 3 : 1) fwd_co
 // exactly the partners Z[Nc-k] of its five outputs (digit complement: 1249-k2 <-> (9-t0,24-t1,4-t2)).
 // N1C: row count as a compile-time constant (0 = from the arguments).  HALVED: the 1/2 of the real
 // split was already folded into the column pass (Pass1Args::out_scale).
-// WPC: stages 0 and 1 with one warp per tile column (the warp that fetched the row): they only touch
-// that column, so __syncwarp replaces the block barrier between them and a warp starts as soon as
-// ITS row has landed; the 8-column lane interleave is kept for the last stage only, where it makes
-// the global stores 32-byte sectors.
-// W_1250^{32 it t} literals for stage 0 of the row pass (TW0C below)
+// W_1250^{32 it t} literals for stage 0 of the row pass
 __device__ constexpr float kRowsTw0[3][4][2] = {
     {{9.870916009e-01f, -1.601568460e-01f}, {9.486995935e-01f, -3.161789477e-01f}, {8.000617623e-01f, -5.999176502e-01f}, {2.801976204e-01f, -9.599423409e-01f}},
     {{9.486995935e-01f, -3.161789477e-01f}, {8.000617623e-01f, -5.999176502e-01f}, {2.801976204e-01f, -9.599423409e-01f}, {-8.429785967e-01f, -5.379471183e-01f}},
     {{8.858151436e-01f, -4.640382826e-01f}, {5.693368912e-01f, -8.221042752e-01f}, {-3.517109454e-01f, -9.361086488e-01f}, {-7.525988221e-01f, 6.584793329e-01f}},
 };
 
-// ILP0: stage-0 butterflies of a thread handled together (all loads first, then the arithmetic): 0 = the plain loop.
-// TW0C: stage-0 twiddles W^{j t}, j = ul + 32 it, as (4 values loaded once per thread) x (literal W^{32 it t}) instead of 4 loads
-// per butterfly: 12 fewer shared-memory loads per thread in the stage that ncu shows throttled by the MIO queue.
-// TW1C: stage-1 twiddles W_125^{j t}, t = 5a + b, from 8 loaded powers (b = 1..4, 5a = 5..20) and 16 products instead of 24 loads
-// (measured: 6.62 vs 6.55 us per block -- stage 1 is not short of MIO slots -- so off).  TW0C: 6.80 -> 6.55.
-template <bool REAL_SPLIT, int N1C = 0, bool HALVED = false, bool WPC = false, int ILP0 = 0, bool TW0C = true, bool TW1C = false>
+// Stage-0 twiddles W^{j t}, j = ul + 32 it, are (4 values loaded once per thread) x (literal W^{32 it t}) instead of 4 loads per
+// butterfly (6.80 -> 6.55 us per block).  Variants measured and removed again: warp-per-column stages 0/1 (6.93), stage-0
+// butterflies in groups of 2 / 4 (6.71 / 6.73), stage-1 twiddles by products (6.62), a persistent double-buffered form (7.37).
+// For REAL masters fwd_rows_r50.cuh is the default now; this kernel serves COMPLEX 1296 x 1250 masters and
+// kgpu_set_tuning(10, 6).
+template <bool REAL_SPLIT, int N1C = 0, bool HALVED = false>
 __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTables const tb) {
   using P = S1250v2;
   constexpr int N2 = 1250, PITCH = 1250, T = 256;
@@ -351,7 +290,6 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
     dbg[0] = gtimer();
     dbg[5] = sm_id();
   }
-  int const mblk = a.mid_mod ? blk % a.mid_mod : blk;
   // which global row sits in which tile column
   auto row_of = [&](int col, int first = -1) -> int {
     RowItem const it = row_item((first < 0 ? item0 : first) + (REAL_SPLIT ? col >> 1 : col), n1, REAL_SPLIT);
@@ -368,7 +306,7 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
     mbar_fence_init();
     if (row >= 0) {
       mbar_expect_tx(&bars[warp], N2 * 8);
-      bulk_g2s(tile + warp * PITCH, a.mid + ((long)mblk * n1 + row) * a.mid_ld, N2 * 8, &bars[warp]);
+      bulk_g2s(tile + warp * PITCH, a.mid + ((long)blk * n1 + row) * a.mid_ld, N2 * 8, &bars[warp]);
     }
     if (warp == 0) {
       constexpr uint32_t TWB = (uint32_t)((static_tw_count<P>() + 1) & ~1) * 8u;
@@ -381,7 +319,7 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
       if (ty < gridDim.y) {
         int const prow = row_of(warp, tx * IPC);
         int const pblk = a.rev ? gridDim.y - 1 - ty : ty;
-        if (prow >= 0) bulk_prefetch_l2(a.mid + ((long)(a.mid_mod ? pblk % a.mid_mod : pblk) * n1 + prow) * a.mid_ld, N2 * 8);
+        if (prow >= 0) bulk_prefetch_l2(a.mid + ((long)pblk * n1 + prow) * a.mid_ld, N2 * 8);
       }
     }
   }
@@ -389,73 +327,12 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
   int const c = tid & 7, ul = tid >> 3;  // column, butterfly lane 0..31
   bool const col_ok = row_of(c) >= 0;
   mbar_wait(&tbar, 0);
-  if (!WPC && col_ok) mbar_wait(&bars[c], 0);
+  if (col_ok) mbar_wait(&bars[c], 0);
   if (dbg && tid == 0) dbg[1] = gtimer();
   float2 *mycol = tile + c * PITCH;
 
-  if (WPC) {
-    if (row_of(warp) >= 0) {  // warp-uniform
-      mbar_wait(&bars[warp], 0);
-      float2 *col = tile + warp * PITCH;
-#pragma unroll 2
-      for (int j = lane; j < S0; j += 32) {  // stage 0: radix 10, stride 125
-        float2 *p = col + j;
-        float2 x[R0], w[R0];
-#pragma unroll
-        for (int m = 0; m < R0; m++) x[m] = p[m * S0];
-        load_stage_twiddles<R0, S0>(s_tw, j, w);
-        Dft<R0, false>::run(x);
-        p[0] = x[0];
-#pragma unroll
-        for (int t = 1; t < R0; t++) p[t * S0] = cmul(x[t], w[t]);
-      }
-      __syncwarp();
-      float2 const *tw1 = s_tw + P::tw_off(1);
-#pragma unroll 1
-      for (int u = lane; u < N2 / R1; u += 32) {  // stage 1: radix 25, 10 blocks of 125, stride 5
-        int const b = u / S1, j = u - b * S1;
-        float2 *p = col + b * NSUB1 + j;
-        float2 x[R1];
-#pragma unroll
-        for (int m = 0; m < R1; m++) x[m] = p[m * S1];
-        Dft<R1, false>::run(x);
-#pragma unroll
-        for (int t = 1; t < R1; t++) x[t] = cmul(x[t], tw1[(t - 1) * S1 + j]);
-#pragma unroll
-        for (int t = 0; t < R1; t++) p[t * S1] = x[t];
-      }
-    }
-  }
   // ---- stage 0: radix 10, stride 125 (125 butterflies per column) ------------------------------
-  if constexpr (ILP0 > 0) if (!WPC && col_ok) {
-    constexpr int IL = ILP0 > 0 ? ILP0 : 1;
-#pragma unroll
-    for (int it0 = 0; it0 < 4; it0 += IL) {
-      float2 x[IL][R0];
-#pragma unroll
-      for (int q = 0; q < IL; q++) {
-        int const j = ul + (T / 8) * (it0 + q);
-        if (it0 + q < 3 || j < S0) {
-#pragma unroll
-          for (int m = 0; m < R0; m++) x[q][m] = mycol[j + m * S0];
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < IL; q++) {
-        int const j = ul + (T / 8) * (it0 + q);
-        if (it0 + q < 3 || j < S0) {
-          float2 w[R0];
-          load_stage_twiddles<R0, S0>(s_tw, j, w);
-          Dft<R0, false>::run(x[q]);
-          float2 *p = mycol + j;
-          p[0] = x[q][0];
-#pragma unroll
-          for (int t = 1; t < R0; t++) p[t * S0] = cmul(x[q][t], w[t]);
-        }
-      }
-    }
-  }
-  if constexpr (TW0C && ILP0 == 0) if (!WPC && col_ok) {
+  if (col_ok) {
     float2 base[4];
 #pragma unroll
     for (int q = 0; q < 4; q++) base[q] = s_tw[((1 << q) - 1) * S0 + ul];  // W^{ul t}, t = 1, 2, 4, 8
@@ -482,23 +359,9 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
       }
     }
   }
-  if (!WPC && col_ok && ILP0 == 0 && !TW0C) {
-#pragma unroll 2
-    for (int j = ul; j < S0; j += T / 8) {
-      float2 *p = mycol + j;
-      float2 x[R0], w[R0];
-#pragma unroll
-      for (int m = 0; m < R0; m++) x[m] = p[m * S0];
-      load_stage_twiddles<R0, S0>(s_tw, j, w);
-      Dft<R0, false>::run(x);
-      p[0] = x[0];
-#pragma unroll
-      for (int t = 1; t < R0; t++) p[t * S0] = cmul(x[t], w[t]);
-    }
-  }
-  if (!WPC) __syncthreads();
+  __syncthreads();
   // ---- stage 1: radix 25, 10 blocks of 125, stride 5 (50 butterflies per column) ---------------
-  if (!WPC && col_ok) {
+  if (col_ok) {
     float2 const *tw1 = s_tw + P::tw_off(1);
 #pragma unroll 1
     for (int u = ul; u < N2 / R1; u += T / 8) {
@@ -508,23 +371,8 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
 #pragma unroll
       for (int m = 0; m < R1; m++) x[m] = p[m * S1];
       Dft<R1, false>::run(x);
-      if (TW1C) {
-        float2 wb[5], wa[5];
 #pragma unroll
-        for (int q = 1; q < 5; q++) {
-          wb[q] = tw1[(q - 1) * S1 + j];
-          wa[q] = tw1[(5 * q - 1) * S1 + j];
-        }
-#pragma unroll
-        for (int t = 1; t < R1; t++) {
-          int const a5 = t / 5, b5 = t - 5 * a5;
-          float2 const w = a5 == 0 ? wb[b5] : (b5 == 0 ? wa[a5] : cmul(wa[a5], wb[b5]));
-          x[t] = cmul(x[t], w);
-        }
-      } else {
-#pragma unroll
-        for (int t = 1; t < R1; t++) x[t] = cmul(x[t], tw1[(t - 1) * S1 + j]);
-      }
+      for (int t = 1; t < R1; t++) x[t] = cmul(x[t], tw1[(t - 1) * S1 + j]);
 #pragma unroll
       for (int t = 0; t < R1; t++) p[t * S1] = x[t];
     }
@@ -648,9 +496,9 @@ __global__ void __launch_bounds__(256, 2) fwd_rows_v2(Pass2Args const a, FwdTabl
 // (20) lanes of a warp write contiguous runs.  Shared-memory traffic per point drops from eight
 // accesses to three.  ISB channels need the whole product first and take the v1 path.
 // OSC: instantiated twice so that the default path carries none of the oscillator's registers
-// TWC: stage-0 twiddles W^{lane t}, t = 5a + b, from the loaded powers b = 1..4 and 5a = 5, 10, .. and one product each
-// instead of R0 - 1 loads per lane.  Measured: 2.12 vs 2.13 us per block, 90 instead of 72 registers -> not the default.
-template <class P, bool OSC = false, bool TWC = false>
+// Measured and removed again: stage-0 twiddles by products (2.12 vs 2.13 us per block at 90 instead of 72 registers), an L2
+// prefetch of a later CTA's slices (2.19 .. 2.36 against 2.12).
+template <class P, bool OSC = false>
 __global__ void __launch_bounds__(kChanWarps * 32) chan_v2(ChanArgs const a) {
   static_assert(P::nst == 2, "two-stage plans only");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -678,17 +526,6 @@ __global__ void __launch_bounds__(kChanWarps * 32) chan_v2(ChanArgs const a) {
       constexpr uint32_t TWB = (uint32_t)((static_tw_count<P>() + 1) & ~1) * 8u;
       mbar_expect_tx(&tbar, TWB);
       bulk_g2s(s_tw, c_plans[p0].tw, TWB, &tbar);
-    }
-  }
-  if (a.pf_ctas && lane == 0 && !a.wrap) {  // pull the slice of the warp `pf_ctas` CTAs later in launch order into L2 now
-    int const lin = blockIdx.y * gridDim.x + blockIdx.x + a.pf_ctas;
-    int const ty = lin / gridDim.x, o = (lin - ty * gridDim.x) * kChanWarps + warp;
-    if (ty < gridDim.y && o < a.norder) {
-      ChanDesc const e = a.desc[a.order ? a.order[o] : a.chan_base + o];
-      if (e.plan >= 0 && e.ncopy > 0) {
-        int const elo = e.dir > 0 ? e.q0 : e.q0 - (e.ncopy - 1), lo = elo & ~1;  // exactly the range that warp's copy reads
-        bulk_prefetch_l2(a.spec + (long)ty * a.spec_stride + lo, (uint32_t)(((elo + e.ncopy - lo) + 1) & ~1) * 8u);
-      }
     }
   }
   __syncthreads();
@@ -763,23 +600,8 @@ __global__ void __launch_bounds__(kChanWarps * 32) chan_v2(ChanArgs const a) {
     for (int m = 0; m < R0; m++) x[m] = product(lane + S0 * m);
     Dft<R0, true>::run(x);
     col[lane] = x[0];
-    if (TWC) {
-      constexpr int NA = (R0 - 1) / 5;
-      float2 wb[5], wa[NA + 1];
 #pragma unroll
-      for (int q = 1; q < 5; q++) wb[q] = s_tw[(q - 1) * S0 + lane];
-#pragma unroll
-      for (int q = 1; q <= NA; q++) wa[q] = s_tw[(5 * q - 1) * S0 + lane];
-#pragma unroll
-      for (int t = 1; t < R0; t++) {
-        int const a5 = t / 5, b5 = t - 5 * a5;
-        float2 const w = a5 == 0 ? wb[b5] : (b5 == 0 ? wa[a5] : cmul(wa[a5], wb[b5]));
-        col[lane + S0 * t] = cmulc(x[t], w);
-      }
-    } else {
-#pragma unroll
-      for (int t = 1; t < R0; t++) col[lane + S0 * t] = cmulc(x[t], s_tw[(t - 1) * S0 + lane]);
-    }
+    for (int t = 1; t < R0; t++) col[lane + S0 * t] = cmulc(x[t], s_tw[(t - 1) * S0 + lane]);
   }
   __syncwarp();
   // ---- stage 1 fused with the store: y[n], n = u + R0*t, keep n >= NS - olen ---------------------

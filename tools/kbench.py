@@ -2,7 +2,7 @@
 """A/B micro-benchmark of the three kernels on cfg-2 (run under gpurun).
 
 usage: kbench.py [--blocks B] [--iters K] variant [variant ...]
-a variant is a comma list of key=value tuning knobs (kgpu_set_tuning), e.g. "0=1,1=1" "0=2,1=2";
+a variant is a comma list of key=value tuning knobs (kgpu_set_tuning), e.g. "10=6" "13=4" "14=1,15=-1" (include/ka9q_gpu.h);
 "static=0" selects the generic kernels.  Variants are interleaved round-robin to cancel drift."""
 import argparse, sys, json
 from pathlib import Path
