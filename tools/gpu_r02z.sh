@@ -1,7 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_r02z7.txt 2>&1
-tail -2 gpurun_out/pytest_r02z7.txt
-timeout 600 python tools/ab_check.py 13=4 10=6 > gpurun_out/ab_r02z7.txt 2>&1
-timeout 900 python tools/kbench.py --blocks 32 default 10=6 13=4 > gpurun_out/kbench_r02z7.txt 2>&1
-cat gpurun_out/ab_r02z7.txt gpurun_out/kbench_r02z7.txt
+for k in 1 2 3; do
+  timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --filter-h-blocks-per-write $k > gpurun_out/fh_k$k.json 2> gpurun_out/fh_k$k.err
+  python - <<PY
+import json
+d=json.loads(open("gpurun_out/fh_k$k.json").read().strip().splitlines()[-1])
+f=d["e2e"]["filter_h"]; print("k=$k", round(f["value"]), f["ms_per_block"], f["latency_ms_mean"], f["latency_ms_max"], f["dropped_blocks"], f.get("parity"), round(f["with_ring_memcpy"]["value"]))
+PY
+done
