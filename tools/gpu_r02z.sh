@@ -1,5 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python tools/ab_check.py 9=1 > gpurun_out/ab_r02z8.txt 2>&1
-timeout 900 python tools/kbench.py --blocks 32 default 9=1 > gpurun_out/kbench_r02z8.txt 2>&1
-head -3 gpurun_out/ab_r02z8.txt; cat gpurun_out/kbench_r02z8.txt
+timeout 400 compute-sanitizer --tool memcheck --print-limit 20 python tools/kbench.py --blocks 2 --iters 1 --rounds 1 default > gpurun_out/sanitizer_cfg2.txt 2>&1
+echo "rc=$?" >> gpurun_out/sanitizer_cfg2.txt
+timeout 400 compute-sanitizer --tool memcheck --print-limit 20 python tools/kbench.py --config cfg4 --blocks 2 --iters 1 --rounds 1 default > gpurun_out/sanitizer_cfg4.txt 2>&1
+echo "rc=$?" >> gpurun_out/sanitizer_cfg4.txt
+tail -6 gpurun_out/sanitizer_cfg2.txt; tail -6 gpurun_out/sanitizer_cfg4.txt
