@@ -371,36 +371,17 @@ def run_ours(args) -> None:
         a_send = [torch.zeros((world, Bq, width), dtype=torch.complex64, device=dev) for _ in range(nslots)]
         a_recv = [torch.empty((world, Bq, width), dtype=torch.complex64, device=dev) for _ in range(nslots)]
 
-        # The ranks' windows sit at a regular spacing in a spectrum (contiguous channel groups of equal width), so the pack of
-        # all `world` windows of a rank's blocks and the unpack of all peers' blocks are ONE strided device copy each (the step
-        # is paced by host-side issue at 4-8 GPUs: 2 copies instead of 2 x world per step).
-        stride = cz.master.spec_stride
-        los = [lo for lo, _ in lo_hi]
-        gap = los[1] - los[0] if world > 1 else 0
-        regular = all(los[q] == los[0] + q * gap for q in range(world)) and gap > 0 and los[-1] + width <= stride
+        from ka9q_radio_b200.sharding import SliceExchange
+        sx = SliceExchange(rank, world, lo_hi, cz.master.spec_stride, Bq)   # pack / unpack: one strided copy each when regular
 
         def fwd_part(step, slot):
             mine = spec2[slot][rank * Bq:(rank + 1) * Bq]
             cz.forward(d_stream, Bq, mine, scale=w.scale, first_block=(step % ngroups) * B + rank * Bq)
-            if regular:   # view (peer, block, bin) of this rank's Bq spectra
-                a_send[slot].copy_(torch.as_strided(mine, (world, Bq, width), (gap, stride, 1), mine.storage_offset() + los[0]))
-            else:
-                for q in range(world):
-                    lo, hi = lo_hi[q]
-                    a_send[slot][q, :, : hi - lo].copy_(mine[:, lo:hi])
+            sx.pack(mine, a_send[slot])
 
         def exchange(slot):
             h = dist.all_to_all_single(a_recv[slot].view(-1), a_send[slot].view(-1), async_op=True)
-            lo, hi = lo_hi[rank]
-
-            def unpack():
-                if regular:   # view (producer, block, bin) of the whole spectrum ring slot, this rank's window only
-                    sp = spec2[slot]
-                    torch.as_strided(sp, (world, Bq, width), (Bq * stride, stride, 1), sp.storage_offset() + lo).copy_(a_recv[slot])
-                else:
-                    for p in range(world):
-                        spec2[slot][p * Bq:(p + 1) * Bq, lo:hi].copy_(a_recv[slot][p, :, : hi - lo])
-            return _Multi([h], then=unpack)
+            return _Multi([h], then=lambda: sx.unpack(spec2[slot], a_recv[slot]))
 
         sharder = PipelinedSharder(rank, world, forward=fwd_part, channels=chan, depth=nslots, forward_on_all=True, broadcast=exchange)
         par = (f"{world} GPUs: every rank transforms {Bq} of the step's {B} blocks and sends each peer only the bins its channels "

@@ -60,6 +60,55 @@ class PipelinedSharder:
 
 
 @dataclass
+class SliceExchange:
+    """Block-parallel forward + slice hand-off (bench.py --mg-mode a2a): every rank transforms `blocks_per_rank` of a step's
+    blocks and ONE all-to-all sends each peer only the bins that peer's channels read.
+
+    windows[r] = (lo, hi): the bin range rank r's channels read (slave walk, reference filter.c:728-893, plus the half
+    transform on either side).  send / recv buffers are (world, blocks_per_rank, width) complex tensors; a step's spectra are
+    rows p*blocks_per_rank + b of a (world*blocks_per_rank, spec_stride) tensor.  When the windows are regularly spaced (equal
+    contiguous channel groups) the pack and the unpack are one strided copy each instead of `world` copies: at 4-8 GPUs the
+    step is paced by the host issuing launches, not by the GPUs."""
+
+    rank: int
+    world: int
+    windows: Sequence[tuple[int, int]]
+    spec_stride: int
+    blocks_per_rank: int
+
+    def __post_init__(self):
+        self.width = max(hi - lo for lo, hi in self.windows)
+        los = [lo for lo, _ in self.windows]
+        self.gap = los[1] - los[0] if self.world > 1 else 0
+        self.regular = (self.world > 1 and self.gap > 0 and all(los[q] == los[0] + q * self.gap for q in range(self.world))
+                        and los[-1] + self.width <= self.spec_stride)
+
+    def pack(self, mine, send) -> None:
+        """mine: this rank's (blocks_per_rank, spec_stride) spectra -> send[q, b, :] = mine[b, lo_q : lo_q + width]"""
+        import torch
+
+        if self.regular:
+            send.copy_(torch.as_strided(mine, (self.world, self.blocks_per_rank, self.width), (self.gap, self.spec_stride, 1),
+                                        mine.storage_offset() + self.windows[0][0]))
+            return
+        for q, (lo, hi) in enumerate(self.windows):
+            send[q, :, : hi - lo].copy_(mine[:, lo:hi])
+
+    def unpack(self, spectra, recv) -> None:
+        """recv[p, b, :] (from rank p) -> spectra[p*blocks_per_rank + b, lo : hi] for this rank's window"""
+        import torch
+
+        lo, hi = self.windows[self.rank]
+        if self.regular:
+            torch.as_strided(spectra, (self.world, self.blocks_per_rank, self.width),
+                             (self.blocks_per_rank * self.spec_stride, self.spec_stride, 1), spectra.storage_offset() + lo).copy_(recv)
+            return
+        n = self.blocks_per_rank
+        for p in range(self.world):
+            spectra[p * n:(p + 1) * n, lo:hi].copy_(recv[p, :, : hi - lo])
+
+
+@dataclass
 class MulticastSharder:
     """Spectrum hand-off through an NVSwitch multicast mapping instead of a collective call.
 

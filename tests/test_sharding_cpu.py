@@ -99,6 +99,57 @@ def _worker(rank, world, port, tmp):
                     out[(step * world + r, i)] = O.channel_block(O.KO_REAL, X, resp[i], chans[i]["shift"])[-48:].copy()
 
         PipelinedSharder(rank, world, forward_part, gather, channels_ag, forward_on_all=True).run(range(nst))
+    elif os.environ.get("KA_SHARDER", "").startswith("a2a"):
+        # block-parallel forward + slice hand-off (bench.py --mg-mode a2a): rank r transforms block step*world + r and ONE
+        # all-to-all gives every rank the bins ITS channels read of every block of the step.  "a2a" puts the channel groups at
+        # a regular spacing (one strided copy per pack / unpack), "a2a-irregular" does not (one copy per peer).
+        from ka9q_radio_b200.sharding import SliceExchange
+
+        if os.environ["KA_SHARDER"] == "a2a":
+            chans = [dict(olen=48, shift=600 + 150 * i, low=-0.3, high=0.3, beta=9.0) for i in range(8)]
+        else:   # second group's window + the common width would run past the spectrum: per-peer copies
+            chans = [dict(olen=48, shift=sh, low=-0.3, high=0.3, beta=9.0) for sh in (300, 700, 1100, 1500, 2700, 2800, 2900)]
+        resp = {i: O.design_response(60, 48, N, True, -0.3, 0.3, 9.0) for i in range(len(chans))}
+        groups = channel_groups(len(chans), world)
+        mine = groups[rank]
+        nb = N // 2 + 1
+        stride = (nb + 3) // 4 * 4
+        win = []
+        for g in groups:
+            sh = [chans[i]["shift"] for i in g]
+            win.append((max(0, min(sh) - 32), min(nb, max(sh) + 32)))
+        sx = SliceExchange(rank, world, win, stride, 1)
+        assert sx.regular == (os.environ["KA_SHARDER"] == "a2a")
+        nst = nsteps // world
+        spec2 = [torch.full((world, stride), float("nan"), dtype=torch.complex64) for _ in range(2)]
+        send = [torch.zeros((world, 1, sx.width), dtype=torch.complex64) for _ in range(2)]
+        recv = [torch.zeros((world, 1, sx.width), dtype=torch.complex64) for _ in range(2)]
+
+        def forward_part(step, slot):
+            spec2[slot].fill_(float("nan"))   # a bin nobody sent would poison the channel outputs
+            own = spec2[slot][rank:rank + 1]
+            own[0, :nb].copy_(torch.from_numpy(O.forward(O.block_window(x, L, M, step * world + rank))))
+            sx.pack(own, send[slot])
+
+        class _Then:
+            def __init__(self, h, fn):
+                self.h, self.fn = h, fn
+
+            def wait(self):
+                self.h.wait()
+                self.fn()
+
+        def exchange(slot):
+            h = dist.all_to_all_single(recv[slot].view(-1), send[slot].view(-1), async_op=True)
+            return _Then(h, lambda: sx.unpack(spec2[slot], recv[slot]))
+
+        def channels_a2a(step, slot):
+            for r in range(world):
+                X = spec2[slot][r, :nb].numpy()
+                for i in mine:
+                    out[(step * world + r, i)] = O.channel_block(O.KO_REAL, X, resp[i], chans[i]["shift"])[-48:].copy()
+
+        PipelinedSharder(rank, world, forward_part, exchange, channels_a2a, forward_on_all=True).run(range(nst))
     else:
         PipelinedSharder(rank, world, forward, broadcast, channels).run(range(nsteps))
     np.save(Path(tmp) / f"rank{rank}.npy", {k: v for k, v in out.items()}, allow_pickle=True)
@@ -106,12 +157,12 @@ def _worker(rank, world, port, tmp):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("sharder", ["pipelined", "multicast", "allgather"])
+@pytest.mark.parametrize("sharder", ["pipelined", "multicast", "allgather", "a2a", "a2a-irregular"])
 def test_two_rank_gloo_pipeline_matches_single_process(tmp_path, oracle, sharder, monkeypatch):
     import torch.multiprocessing as mp
 
     monkeypatch.setenv("KA_SHARDER", sharder)
-    port = 29600 + (os.getpid() % 300) + {"pipelined": 0, "multicast": 17, "allgather": 31}[sharder]
+    port = 29600 + (os.getpid() % 300) + {"pipelined": 0, "multicast": 17, "allgather": 31, "a2a": 43, "a2a-irregular": 59}[sharder]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     got = {}
     for r in range(2):
@@ -119,8 +170,12 @@ def test_two_rank_gloo_pipeline_matches_single_process(tmp_path, oracle, sharder
     L, M, nsteps = 4800, 1201, 5
     x = oracle.siggen_real(nsteps * L, 0.1, 0.02, 0.27, 1.0)
     chans = [dict(olen=48, shift=900 + 200 * i, low=-0.3, high=0.3, beta=9.0) for i in range(7)]
+    if sharder == "a2a":
+        chans = [dict(olen=48, shift=600 + 150 * i, low=-0.3, high=0.3, beta=9.0) for i in range(8)]
+    if sharder == "a2a-irregular":
+        chans = [dict(olen=48, shift=sh, low=-0.3, high=0.3, beta=9.0) for sh in (300, 700, 1100, 1500, 2700, 2800, 2900)]
     ref, _ = oracle.run_stream(x, L, M, chans)
-    nexp = nsteps if sharder != "allgather" else (nsteps // 2) * 2
+    nexp = nsteps if sharder in ("pipelined", "multicast") else (nsteps // 2) * 2
     assert len(got) == nexp * len(chans)
     for (step, i), y in got.items():
         assert np.array_equal(y, ref[step][i])
