@@ -35,6 +35,8 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC = "input Msamples/s through forward+filter+inverse at N channels"
+L2_BYTES = 126e6   # B200 L2 (B200_PROFILING.md); the resident input a rank cycles through must exceed it
+
 
 
 class ClockSampler:
@@ -306,6 +308,10 @@ def run_ours(args) -> None:
     alg_chan = alg_bytes - alg_fwd_in - alg_fwd_out
 
     # ---- inputs: a stream larger than L2, resident in HBM before the timed region ----------
+    # block-parallel modes: a rank only reads B/world of a step's windows, so the resident stream is lengthened until the part
+    # a rank cycles through is larger than L2 as well (8 GPUs: 256 blocks = 1.3 GB per GPU)
+    rank_reads = (B // world if world > 1 and args.mg_mode in ("allgather", "a2a") else B) * wpb * 2   # bytes per step
+    nstream = max(nstream, B * int(np.ceil(1.25 * L2_BYTES / rank_reads)))
     host = w.stream(nstream)
     hpin = torch.from_numpy(np.concatenate([np.zeros(hist, np.int16), host])).pin_memory()
     d_stream = hpin.to(dev)
@@ -560,7 +566,8 @@ def run_ours(args) -> None:
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w.description + (" per GPU" if world > 1 else ""),
                    "blocks_per_step": B, "input_stream_MB": round(host.nbytes / 1e6, 1),
-                   "l2_policy": "input stream larger than L2 (126 MB), consecutive groups cycled; no explicit flush",
+                   "l2_policy": f"input stream larger than L2 (126 MB) -- this rank cycles through {rank_reads * (nstream // B) / 1e6:.0f} MB "
+                                "of it --, consecutive groups cycled; no explicit flush",
                    "plan": cz.master.describe(), "parallelism": par,
                    "value_definition": ("input stream rate" if world == 1 else
                                         "channel-weighted: stream rate x GPUs (every GPU runs the whole sample stream through its own "
